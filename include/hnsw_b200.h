@@ -1,0 +1,165 @@
+/*
+ * hnsw_b200.h -- C ABI of the B200-native HNSW hot path (libhnsw_b200.so).
+ *
+ * Drop-in boundary for ONE path of dhwodnjs/pgvector-hnsw-partitioning: distance evaluation for
+ * the vector_l2_ops / vector_ip_ops / vector_cosine_ops (and halfvec_*) operator classes inside
+ * HNSW search and index build, the hnswbuild insert path, the hnswgettuple scan path, and
+ * partition routing / top-k merge.
+ *
+ * Citations: the reference mount contains no source (/root/reference/README.md:1, "# pg", is the
+ * whole tree), so no reference file:line can be given.  Each entry point names the PostgreSQL
+ * index-AM callback or upstream-pgvector function [RECALL] whose role it takes; INTEGRATION.md
+ * shows the Postgres-side glue a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  "host" pointers are ordinary CPU
+ * memory owned by the caller; "dev" pointers are CUDA device memory on the index's GPU.  Every
+ * function returning int returns 0 (or a count) on success and a negative HB_E* code on failure;
+ * hb_last_error() gives the message (Postgres glue turns it into ereport(ERROR)).  One handle is
+ * not thread-safe; distinct handles are.  There is no CPU fallback: without a CUDA device every
+ * call fails with HB_ECUDA.
+ */
+#ifndef HNSW_B200_H
+#define HNSW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* operator classes: FUNCTION 1 (HNSW_DISTANCE_PROC) of the opclass */
+enum {
+    HB_L2 = 0,     /* vector_l2_ops / halfvec_l2_ops         : vector_l2_squared_distance       */
+    HB_IP = 1,     /* vector_ip_ops / halfvec_ip_ops         : vector_negative_inner_product    */
+    HB_COSINE = 2  /* vector_cosine_ops / halfvec_cosine_ops : normalise (FUNCTION 2) + neg. ip */
+};
+enum { HB_F32 = 0 /* vector */, HB_F16 = 1 /* halfvec */ };
+
+enum {
+    HB_OK = 0,
+    HB_EINVAL = -1,    /* bad argument (dimension, m, ef_construction range, NULL pointer ...) */
+    HB_ECUDA = -2,     /* CUDA runtime failure or no device */
+    HB_ENOMEM = -3,    /* capacity exceeded / allocation failed */
+    HB_ESTATE = -4,    /* call order (gettuple before rescan ...) */
+    HB_ELIMIT = -5     /* more than HB_TIE_LIMIT exactly-equal distances at the ef boundary */
+};
+
+#define HB_HEAPTIDS 10     /* HNSW_HEAPTIDS: duplicate heap TIDs kept per element */
+#define HB_MAX_DIM 16000   /* halfvec limit; vector is 2000 in pgvector's hnsw */
+#define HB_TIE_LIMIT 4096
+
+typedef struct hb_index hb_index;   /* one HNSW index = one partition, resident on one GPU  */
+typedef struct hb_scan hb_scan;     /* IndexScanDesc->opaque (HnswScanOpaque)               */
+
+typedef struct {
+    int64_t n_dist;    /* query<->element distance evaluations */
+    int64_t n_hop0;    /* elements expanded on layer 0         */
+    int64_t n_hopu;    /* elements expanded on layers >= 1     */
+    int64_t n_pair;    /* element<->element evaluations in neighbour selection (build) */
+    int64_t n_slow;    /* queries re-run on the large-visited-set path */
+} hb_counters;
+
+const char *hb_last_error(void);
+const char *hb_version(void);
+/* number of CUDA devices, or HB_ECUDA */
+int hb_device_count(void);
+
+/* ---- index lifetime: hnswhandler reloptions (m, ef_construction) + opclass ---------------- */
+/* m in [2,100], ef_construction in [4,1000] and >= 2m (hnsw.c reloption checks).  capacity =
+ * maximum number of elements; seed drives the level draw of HnswInitElement. */
+hb_index *hb_index_create(int device, int dim, int m, int ef_construction, int metric, int dtype,
+                          int64_t capacity, uint64_t seed);
+void hb_index_free(hb_index *ix);
+int64_t hb_index_size(const hb_index *ix);          /* elements */
+int hb_index_entry(const hb_index *ix, int32_t *entry, int *entry_level);
+
+/* ---- ambuild (hnswbuild) / aminsert (hnswinsert) -------------------------------------------- */
+/* Insert n tuples (vecs: n x dim of the index dtype, host; heap_tids NULL = row number).
+ * hb_build on an empty index is the CREATE INDEX heap scan; hb_insert appends to a live index.
+ * NULL vectors are the caller's to skip (as pgvector's BuildCallback does); zero-norm vectors are
+ * skipped under HB_COSINE.  Returns the number of tuples indexed, or a negative error. */
+int64_t hb_build(hb_index *ix, const void *host_vecs, int64_t n, const int64_t *heap_tids);
+int64_t hb_insert(hb_index *ix, const void *host_vecs, int64_t n, const int64_t *heap_tids);
+/* batch size of the GPU insert pipeline (0 = automatic) */
+int hb_set_build_batch(hb_index *ix, int max_batch);
+/* HnswInitElement's level draw for the seq-th initialised element: (int)(-ln(U) / ln(m)), capped */
+int hb_level_for(uint64_t seed, int64_t seq, int m);
+/* tuning knobs: "slots" (visited-table size), "grid" (CTA cap), "build_batch",
+ * "per_query_counters" (0/1).  0 restores the automatic choice. */
+int hb_set_option(hb_index *ix, const char *name, int value);
+
+/* ---- flat graph image (the layout in HBM; DESIGN.md "Data layout") ------------------------- */
+/* Load a graph built elsewhere (e.g. by the CPU oracle, or converted from pgvector index pages).
+ * vecs n x dim (normalised already when cosine); level n; nbr0 n x 2m (-1 pad); uoff n (row into
+ * nbru or -1); nbru upper_rows x m; ntids n (NULL = all 1); tids n x HB_HEAPTIDS (NULL = id). */
+int hb_index_load(hb_index *ix, int64_t n, int64_t upper_rows, int32_t entry, const void *vecs,
+                  const uint8_t *level, const int32_t *nbr0, const int32_t *uoff,
+                  const int32_t *nbru, const uint8_t *ntids, const int64_t *tids);
+int64_t hb_index_upper_rows(const hb_index *ix);
+/* any pointer may be NULL */
+int hb_index_export(const hb_index *ix, void *vecs, uint8_t *level, int32_t *nbr0, int32_t *uoff,
+                    int32_t *nbru, uint8_t *ntids, int64_t *tids);
+
+/* ---- ambeginscan / amrescan / amgettuple / amendscan (hnswscan.c) -------------------------- */
+hb_scan *hb_beginscan(hb_index *ix);
+/* bind the ORDER BY query vector (dim components of the index dtype) and hnsw.ef_search */
+int hb_rescan(hb_scan *scan, const void *host_query, int ef_search);
+/* next-nearest heap TID: 1 = produced, 0 = exhausted, <0 = error.  Forward scans only. */
+int hb_gettuple(hb_scan *scan, int64_t *heap_tid, float *distance);
+void hb_endscan(hb_scan *scan);
+
+/* ---- batched scan (the extension a GPU needs: many amrescan+amgettuple at once) ------------ */
+/* host buffers in, host buffers out; H2D and D2H copies happen inside.  For each of nq queries
+ * writes the first k heap TIDs nearest-first (pad: -1 / +inf) and the count. */
+int hb_search_batch(hb_index *ix, const void *host_queries, int64_t nq, int ef_search, int k,
+                    int64_t *out_tids, float *out_dist, int32_t *out_cnt);
+/* as above but returns elements (graph node ids), ef per query: out_elem/out_dist nq x ef */
+int hb_search_batch_elements(hb_index *ix, const void *host_queries, int64_t nq, int ef_search,
+                             int32_t *out_elem, float *out_dist, int32_t *out_cnt);
+/* device-resident: queries already in HBM (nq x dim, index dtype), results left in HBM;
+ * asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream).
+ * dev_out_elem / dev_out_dist: nq x ef; dev_out_cnt: nq. */
+int hb_search_batch_dev(hb_index *ix, const void *dev_queries, int64_t nq, int ef_search,
+                        int32_t *dev_out_elem, float *dev_out_dist, int32_t *dev_out_cnt,
+                        void *stream);
+/* one HnswSearchLayer call from explicit entry points (unit-test surface of the layer kernel):
+ * ep nq x nep element ids; out nq x max(ef,nep) */
+int hb_search_layer(hb_index *ix, const void *host_queries, int64_t nq, const int32_t *ep, int nep,
+                    int ef, int layer, int32_t *out_elem, float *out_dist, int32_t *out_cnt);
+/* counters accumulated since the last reset (algorithmic bytes for the roofline come from these) */
+int hb_get_counters(hb_index *ix, hb_counters *out, int reset);
+/* per-query counters of the last batch (needs option per_query_counters = 1): nq x 4 int32 =
+ * n_dist, n_hop0, n_hopu, 1 if the query ran on the large-visited-set path */
+int hb_get_per_query_counters(hb_index *ix, int64_t nq, int32_t *out);
+/* device time (ms) of the most recent search kernel launch sequence on the index's own events */
+float hb_last_search_ms(const hb_index *ix);
+
+/* ---- opclass support functions, batched --------------------------------------------------- */
+/* FUNCTION 1: distances from each of nq queries to its own list of nc candidate elements
+ * (cand nq x nc, ids < 0 give +inf).  The query-vs-neighbour-list kernel on its own. */
+int hb_distance_batch(hb_index *ix, const void *host_queries, int64_t nq, const int32_t *cand,
+                      int nc, float *out_dist);
+/* FUNCTION 2 + l2_normalize: n x dim in, n x dim out (index dtype), ok[i] = 0 for zero norm */
+int hb_normalize(hb_index *ix, const void *host_in, int64_t n, void *host_out, uint8_t *ok);
+
+/* ---- exact scan of a partition (recall ground truth; bf16 tcgen05 GEMM + fp32 re-rank) ------ */
+int hb_bruteforce(hb_index *ix, const void *host_queries, int64_t nq, int k, int32_t *out_elem,
+                  float *out_dist);
+
+/* ---- partition routing / merge -------------------------------------------------------------- */
+/* partition of a heap TID / row id: splitmix64(id) mod n_partitions */
+int hb_partition_of(int64_t id, int n_partitions);
+void hb_partition_route(const int64_t *ids, int64_t n, int n_partitions, int32_t *out_part);
+/* merge P per-partition top-k lists (dev_tids / dev_dist: P x nq x k, nearest-first, pad -1/+inf)
+ * into nq x k on the device; asynchronous on stream. */
+int hb_merge_topk_dev(int device, const int64_t *dev_tids, const float *dev_dist, int n_parts,
+                      int64_t nq, int k, int64_t *dev_out_tids, float *dev_out_dist, void *stream);
+/* map element ids to the first k heap TIDs on the device (nq x ef elements -> nq x k tids) */
+int hb_elements_to_tids_dev(hb_index *ix, const int32_t *dev_elem, const float *dev_dist,
+                            int64_t nq, int ef, int k, int64_t *dev_out_tids, float *dev_out_dist,
+                            void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,207 @@
+// distance.cuh -- warp-cooperative distance evaluation in the canonical summation order.
+//
+// Takes the role of pgvector's opclass FUNCTION 1 support functions: VectorL2SquaredDistance /
+// VectorInnerProduct (vector.c) and HalfvecL2SquaredDistance / HalfvecInnerProduct (halfutils.c)
+// [RECALL; the reference mount has no source, /root/reference/README.md:1].
+//
+// Canonical order (restated on the CPU by oracle/hnsw_oracle.c canon_l2/canon_ip so results can
+// be compared bit-for-bit):
+//   * a row is a sequence of 16-byte chunks (VEC = 4 fp32 or 8 fp16 components);
+//   * lane l of the warp owns chunks l, l+32, l+64, ... and keeps VEC fp32 accumulators, one per
+//     component slot, each an FMA chain in increasing chunk order;
+//   * the lane's accumulators fold pairwise: (a0+a1)+(a2+a3) [+ the same for a4..a7];
+//   * the 32 lane partials fold by the xor-butterfly 16, 8, 4, 2, 1.
+// Several candidates are evaluated per pass (G rows in flight per lane as 128-bit loads) and
+// reduced together by a transposed butterfly, which performs the same additions in the same order.
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace hb {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// 128-bit streaming load of vector data: read-only path, do not allocate in L1 (rows are touched
+// once per query; L2 keeps the hubs).
+__device__ __forceinline__ uint4 ldg_stream(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+template <typename T> struct Vec;
+template <> struct Vec<float> { static constexpr int VEC = 4; };
+template <> struct Vec<__half> { static constexpr int VEC = 8; };
+
+// Query layout in shared memory: fp32 rows: q[4*ch + k]. fp16 rows: two planes so that each
+// lane's 128-bit read is bank-conflict free: q[4*ch + k] (k<4) and q[plane + 4*ch + (k-4)].
+template <typename T> __device__ __forceinline__ int query_floats(int nvec) { return nvec * Vec<T>::VEC; }
+
+template <typename T, bool IP>
+__device__ __forceinline__ void accum_chunk(float (&acc)[Vec<T>::VEC], const uint4 &raw, const float *q,
+                                            int ch, int plane)
+{
+    if constexpr (sizeof(T) == 4) {
+        const float4 qv = *reinterpret_cast<const float4 *>(q + 4 * ch);
+        const float v0 = __uint_as_float(raw.x), v1 = __uint_as_float(raw.y);
+        const float v2 = __uint_as_float(raw.z), v3 = __uint_as_float(raw.w);
+        if constexpr (IP) {
+            acc[0] = fmaf(qv.x, v0, acc[0]);
+            acc[1] = fmaf(qv.y, v1, acc[1]);
+            acc[2] = fmaf(qv.z, v2, acc[2]);
+            acc[3] = fmaf(qv.w, v3, acc[3]);
+        } else {
+            float t;
+            t = qv.x - v0; acc[0] = fmaf(t, t, acc[0]);
+            t = qv.y - v1; acc[1] = fmaf(t, t, acc[1]);
+            t = qv.z - v2; acc[2] = fmaf(t, t, acc[2]);
+            t = qv.w - v3; acc[3] = fmaf(t, t, acc[3]);
+        }
+    } else {
+        const float4 qa = *reinterpret_cast<const float4 *>(q + 4 * ch);
+        const float4 qb = *reinterpret_cast<const float4 *>(q + plane + 4 * ch);
+        const float2 h0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+        const float2 h1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+        const float2 h2 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.z));
+        const float2 h3 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.w));
+        if constexpr (IP) {
+            acc[0] = fmaf(qa.x, h0.x, acc[0]);
+            acc[1] = fmaf(qa.y, h0.y, acc[1]);
+            acc[2] = fmaf(qa.z, h1.x, acc[2]);
+            acc[3] = fmaf(qa.w, h1.y, acc[3]);
+            acc[4] = fmaf(qb.x, h2.x, acc[4]);
+            acc[5] = fmaf(qb.y, h2.y, acc[5]);
+            acc[6] = fmaf(qb.z, h3.x, acc[6]);
+            acc[7] = fmaf(qb.w, h3.y, acc[7]);
+        } else {
+            float t;
+            t = qa.x - h0.x; acc[0] = fmaf(t, t, acc[0]);
+            t = qa.y - h0.y; acc[1] = fmaf(t, t, acc[1]);
+            t = qa.z - h1.x; acc[2] = fmaf(t, t, acc[2]);
+            t = qa.w - h1.y; acc[3] = fmaf(t, t, acc[3]);
+            t = qb.x - h2.x; acc[4] = fmaf(t, t, acc[4]);
+            t = qb.y - h2.y; acc[5] = fmaf(t, t, acc[5]);
+            t = qb.z - h3.x; acc[6] = fmaf(t, t, acc[6]);
+            t = qb.w - h3.y; acc[7] = fmaf(t, t, acc[7]);
+        }
+    }
+}
+
+template <int VEC> __device__ __forceinline__ float fold_lane(const float (&a)[VEC])
+{
+    if constexpr (VEC == 4) return (a[0] + a[1]) + (a[2] + a[3]);
+    else return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+}
+
+// Lane partials of G candidate rows against the query in shared memory.
+// NV > 0: chunks per lane known at compile time (FULLROW: nvec == 32*NV, no bounds checks);
+// NV == 0: run-time loop (any dimension).
+template <typename T, bool IP, int NV, bool FULLROW, int G>
+__device__ __forceinline__ void group_partials(const char *__restrict__ vecs, size_t row_bytes, int nvec,
+                                               const float *q, const int32_t (&ids)[G], int lane,
+                                               float (&part)[G])
+{
+    constexpr int VEC = Vec<T>::VEC;
+    const int plane = 4 * nvec;
+    float acc[G][VEC];
+#pragma unroll
+    for (int c = 0; c < G; c++)
+#pragma unroll
+        for (int k = 0; k < VEC; k++) acc[c][k] = 0.0f;
+
+    if constexpr (NV > 0) {
+        uint4 raw[G][NV];
+#pragma unroll
+        for (int c = 0; c < G; c++) {
+            const char *row = vecs + (size_t) ids[c] * row_bytes;
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                const int ch = lane + 32 * j;
+                if (FULLROW || ch < nvec) raw[c][j] = ldg_stream(row + 16 * ch);
+                else raw[c][j] = make_uint4(0, 0, 0, 0);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            const int ch = lane + 32 * j;
+            if (FULLROW || ch < nvec) {
+#pragma unroll
+                for (int c = 0; c < G; c++) accum_chunk<T, IP>(acc[c], raw[c][j], q, ch, plane);
+            }
+        }
+    } else {
+        for (int ch = lane; ch < nvec; ch += 32) {
+            uint4 raw[G];
+#pragma unroll
+            for (int c = 0; c < G; c++) raw[c] = ldg_stream(vecs + (size_t) ids[c] * row_bytes + 16 * ch);
+#pragma unroll
+            for (int c = 0; c < G; c++) accum_chunk<T, IP>(acc[c], raw[c], q, ch, plane);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < G; c++) part[c] = fold_lane<VEC>(acc[c]);
+}
+
+// Transposed butterfly: reduces G per-lane partials across the warp with the additions of the
+// canonical butterfly (16, 8, 4, 2, 1).  On return every lane holds the total of candidate
+// c = lane / (32 / G).
+template <int G> struct XReduce {
+    __device__ __forceinline__ static float run(const float (&p)[G], int lane, int bit)
+    {
+        constexpr int H = G / 2;
+        const bool hi = (lane & bit) != 0;
+        float keep[H];
+#pragma unroll
+        for (int i = 0; i < H; i++) {
+            const float send = hi ? p[i] : p[i + H];
+            const float mine = hi ? p[i + H] : p[i];
+            keep[i] = mine + __shfl_xor_sync(FULL, send, bit);
+        }
+        return XReduce<H>::run(keep, lane, bit >> 1);
+    }
+};
+template <> struct XReduce<1> {
+    __device__ __forceinline__ static float run(const float (&p)[1], int lane, int bit)
+    {
+        float s = p[0];
+        for (int b = bit; b >= 1; b >>= 1) s = s + __shfl_xor_sync(FULL, s, b);
+        return s;
+    }
+};
+
+// distances of G candidates; result of candidate c is returned in every lane via out[c]
+template <typename T, bool IP, int NV, bool FULLROW, int G>
+__device__ __forceinline__ float group_distance(const char *__restrict__ vecs, size_t row_bytes, int nvec,
+                                                const float *q, const int32_t (&ids)[G], int lane)
+{
+    float part[G];
+    group_partials<T, IP, NV, FULLROW, G>(vecs, row_bytes, nvec, q, ids, lane, part);
+    const float s = XReduce<G>::run(part, lane, 16);
+    return IP ? -s : s;   // lane (c * 32/G) .. hold candidate c
+}
+
+// stage a query (global, index dtype, `dim` components) into shared memory as fp32 in the
+// layout accum_chunk expects; pads with zeros up to the chunk boundary.
+template <typename T>
+__device__ __forceinline__ void stage_query(const T *__restrict__ src, int dim, int nvec, float *q, int lane)
+{
+    constexpr int VEC = Vec<T>::VEC;
+    const int total = nvec * VEC;
+    for (int e = lane; e < total; e += 32) {
+        float v = 0.0f;
+        if (e < dim) {
+            if constexpr (sizeof(T) == 4) v = src[e];
+            else v = __half2float(src[e]);
+        }
+        if constexpr (sizeof(T) == 4) q[e] = v;
+        else {
+            const int ch = e >> 3, k = e & 7;
+            q[(k < 4 ? 0 : 4 * nvec) + 4 * ch + (k & 3)] = v;
+        }
+    }
+}
+
+}   // namespace hb

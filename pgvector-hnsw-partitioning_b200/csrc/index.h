@@ -1,0 +1,115 @@
+// index.h -- internal definition of the hb_index / hb_scan handles (host side).
+#pragma once
+#include "../../include/hnsw_b200.h"
+#include "search_core.cuh"
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+
+namespace hb {
+
+void set_error(const char *fmt, ...);
+
+#define HB_CK(call)                                                                              \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            hb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return HB_ECUDA;                                                                     \
+        }                                                                                        \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}   // namespace hb
+
+struct hb_index {
+    int device = 0, dim = 0, m = 0, efc = 0, metric = 0, dtype = 0;
+    int esize = 4, nvec = 0, num_sms = 148;
+    size_t row_bytes = 0;
+    int64_t cap = 0, n = 0, seq = 0;
+    uint64_t seed = 0;
+    int64_t upper_rows = 0, upper_cap = 0;
+    int32_t entry = -1;
+    int entry_level = -1;
+    bool has_dups = false;
+
+    // graph image in HBM
+    char *d_vecs = nullptr;
+    int32_t *d_nbr0 = nullptr;
+    float *d_nbr0d = nullptr;      // cached owner->neighbour distances (build only)
+    int32_t *d_uoff = nullptr;
+    int32_t *d_nbru = nullptr;
+    float *d_nbrud = nullptr;
+    int64_t *d_tid0 = nullptr;     // first heap TID of each element
+    uint8_t *d_ntids = nullptr;
+    int64_t *d_tidx = nullptr;     // remaining HB_HEAPTIDS-1 TIDs, allocated when duplicates exist
+
+    // host mirrors of the small per-element state
+    std::vector<uint8_t> h_level, h_ntids;
+    std::vector<int64_t> h_tids;   // n x HB_HEAPTIDS
+
+    // tuning knobs (0 = automatic)
+    int opt_slots = 0, opt_grid = 0, opt_build_batch = 0, opt_per_query = 0;
+
+    // workspaces
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    hb::DevBuf ws_q, ws_qn, ws_elem, ws_dist, ws_cnt, ws_status, ws_slow, ws_misc, ws_pq, ws_tids, ws_tdist;
+    hb::DevBuf ws_gbits, ws_gwd, ws_gwi, ws_ep;
+    hb::DevBuf ws_build[12];
+    unsigned long long *d_totals = nullptr;   // n_dist, n_hop0, n_hopu, n_slow, n_pair, ...
+    hb_counters host_totals = {0, 0, 0, 0, 0};
+    bool timing_valid = false;
+
+    hb::GraphView view() const
+    {
+        hb::GraphView g;
+        g.vecs = d_vecs; g.row_bytes = row_bytes; g.dim = dim; g.nvec = nvec;
+        g.nbr0 = d_nbr0; g.uoff = d_uoff; g.nbru = d_nbru; g.m = m;
+        g.entry = entry; g.entry_level = entry_level; g.n = n;
+        return g;
+    }
+};
+
+struct hb_scan {
+    hb_index *ix = nullptr;
+    std::vector<char> query;
+    int ef = 0;
+    bool bound = false, fetched = false;
+    std::vector<int32_t> elem;
+    std::vector<float> dist;
+    int cnt = 0, pos = 0, tid_pos = -1;
+};
+
+namespace hb {
+// implemented per (dtype, metric) translation unit
+struct ScanParams;
+struct ScanLaunchInfo;
+typedef cudaError_t (*scan_launch_fn)(const ScanParams &, int num_sms, int max_grid, cudaStream_t, ScanLaunchInfo *);
+scan_launch_fn get_scan_launcher(int dtype, bool ip, bool slow);
+
+struct DistBatchParams;
+typedef cudaError_t (*dist_launch_fn)(const DistBatchParams &, cudaStream_t);
+dist_launch_fn get_dist_launcher(int dtype, bool ip);
+
+// build.cu
+int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n, const int64_t *heap_tids);
+int level_for(uint64_t seed, int64_t seq, int m);
+uint64_t splitmix64(uint64_t x);
+}   // namespace hb

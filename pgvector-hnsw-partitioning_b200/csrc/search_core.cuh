@@ -1,0 +1,258 @@
+// search_core.cuh -- one warp runs one query's HnswSearchLayer beam search.
+//
+// Takes the role of hnswutils.c HnswSearchLayer [RECALL / arXiv:1603.09320 Alg. 2; the reference
+// mount has no source, /root/reference/README.md:1].  The CPU formulation keeps two heaps, C
+// (candidates, nearest first) and W (results, furthest first), and a visited hash.  Here:
+//   * W and C are ONE array in shared memory sorted by the key (distance, id), each entry
+//     carrying an "expanded" bit.  C = the unexpanded entries.  The array keeps ef entries plus
+//     the run of entries whose distance EQUALS entry ef-1 (the only evicted candidates that the
+//     CPU loop could still expand: `c->distance > f->distance` is false for them), so the
+//     expansion sequence -- and therefore every id returned -- is identical to the two-heap loop
+//     with (distance, id) tie order (oracle/hnsw_oracle.c search_layer).
+//   * the visited set is an open-addressing hash table in shared memory (exact: when it would
+//     exceed its load limit the query is handed to the large-visited-set path, a bitmap in HBM).
+//   * per expansion the warp reads the neighbour list with one coalesced load, filters it through
+//     the visited set, evaluates the new candidates G rows at a time (distance.cuh) and inserts the
+//     admitted ones in neighbour order, re-testing `d < furthest` before each insertion exactly as
+//     the sequential loop does.
+#pragma once
+#include "distance.cuh"
+
+namespace hb {
+
+constexpr uint32_t EXP_BIT = 0x80000000u;
+constexpr uint32_t ID_MASK = 0x7fffffffu;
+constexpr uint32_t EMPTY = 0xffffffffu;
+
+enum { ST_OK = 0, ST_TABLE = 1, ST_TAIL = 2 };
+
+struct GraphView {
+    const char *vecs;        // n rows, row_bytes each (16-byte multiple, zero padded)
+    size_t row_bytes;
+    int dim, nvec;           // nvec = 16-byte chunks per row
+    const int32_t *nbr0;     // n x 2m, -1 padded
+    const int32_t *uoff;     // n: first row of the element in nbru, or -1
+    const int32_t *nbru;     // upper_rows x m
+    int m;
+    int32_t entry;
+    int entry_level;
+    int64_t n;
+};
+
+struct WList {               // sorted (distance, id) array; warp-uniform bookkeeping
+    float *d;
+    uint32_t *id;
+    int cap, L;
+};
+
+// ---- visited sets ---------------------------------------------------------------------------
+struct VisitedHash {         // shared memory, open addressing, linear probing
+    uint32_t *tab;
+    int slots, shift, count, limit;
+    __device__ __forceinline__ void configure(int s)
+    {
+        slots = s;
+        shift = 32 - (31 - __clz(s));
+        limit = s - (s >> 2);             // 75 % load
+    }
+    __device__ __forceinline__ void clear(int lane)
+    {
+        uint4 *t = reinterpret_cast<uint4 *>(tab);
+        for (int i = lane; i < slots / 4; i += 32) t[i] = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
+        count = 0;
+        __syncwarp();
+    }
+    __device__ __forceinline__ bool room(int incoming) const { return count + incoming <= limit; }
+    __device__ __forceinline__ bool insert(uint32_t key)   // may be called by a subset of lanes
+    {
+        uint32_t h = (key * 0x9E3779B1u) >> shift;
+        for (;;) {
+            const uint32_t old = atomicCAS(tab + h, EMPTY, key);
+            if (old == EMPTY) return true;
+            if (old == key) return false;
+            h = (h + 1) & (slots - 1);
+        }
+    }
+};
+
+struct VisitedBitmap {       // HBM, one bit per element (large-visited-set path)
+    uint32_t *bits;
+    int words, count;
+    __device__ __forceinline__ void configure(int) {}
+    __device__ __forceinline__ void clear(int lane)
+    {
+        for (int i = lane; i < words; i += 32) bits[i] = 0u;
+        count = 0;
+        __syncwarp();
+    }
+    __device__ __forceinline__ bool room(int) const { return true; }
+    __device__ __forceinline__ bool insert(uint32_t key)
+    {
+        const uint32_t bit = 1u << (key & 31);
+        return (atomicOr(bits + (key >> 5), bit) & bit) == 0;
+    }
+};
+
+// ---- W list ---------------------------------------------------------------------------------
+// insert (ed, eid) keeping key order; then trim to ef + boundary ties.  `low` = every entry below
+// it is expanded.
+__device__ __forceinline__ int wlist_insert(WList &w, float ed, uint32_t eid, int ef, int lane, int &low)
+{
+    if (w.L + 1 > w.cap) return ST_TAIL;
+    int pos = 0;
+    for (int base = 0; base < w.L; base += 32) {
+        const int i = base + lane;
+        bool lt = false;
+        if (i < w.L) {
+            const float d = w.d[i];
+            lt = d < ed || (d == ed && (w.id[i] & ID_MASK) < eid);
+        }
+        pos += __popc(__ballot_sync(FULL, lt));
+    }
+    for (int hi = w.L; hi > pos; hi -= 32) {
+        const int lo = max(pos, hi - 32);
+        const int i = lo + lane;
+        const bool act = i < hi;
+        float d = 0.f;
+        uint32_t x = 0u;
+        if (act) { d = w.d[i]; x = w.id[i]; }
+        __syncwarp();
+        if (act) { w.d[i + 1] = d; w.id[i + 1] = x; }
+        __syncwarp();
+    }
+    if (lane == 0) { w.d[pos] = ed; w.id[pos] = eid; }
+    __syncwarp();
+    w.L++;
+    if (w.L > ef) {
+        const float f = w.d[ef - 1];
+        int keep = 0;
+        for (int base = ef; base < w.L; base += 32) {
+            const int i = base + lane;
+            const bool eq = i < w.L && w.d[i] == f;
+            const unsigned b = __ballot_sync(FULL, eq);
+            const int run = (b == FULL) ? 32 : (__ffs(~b) - 1);
+            keep += run;
+            if (run < 32) break;
+        }
+        w.L = ef + keep;
+    }
+    if (pos < low) low = pos;
+    return ST_OK;
+}
+
+// make the first min(L, keep) entries the entry list of the next HnswSearchLayer call: drop the
+// tie tail, clear expanded bits, reset the visited set and mark the entries visited.
+template <typename VS>
+__device__ __forceinline__ void wlist_as_entries(WList &w, VS &vs, int keep, int lane)
+{
+    if (w.L > keep) w.L = keep;
+    vs.clear(lane);
+    for (int base = 0; base < w.L; base += 32) {
+        const int i = base + lane;
+        if (i < w.L) {
+            const uint32_t id = w.id[i] & ID_MASK;
+            w.id[i] = id;
+            vs.insert(id);
+        }
+    }
+    vs.count = w.L;
+    __syncwarp();
+}
+
+struct QueryCounters { int n_dist, n_hop0, n_hopu; };
+
+// distances of the lanes flagged in `mask` (each flagged lane holds a candidate id in nb);
+// result returned in the flagged lane, +inf elsewhere.
+template <typename T, bool IP, int NV, int G>
+__device__ __forceinline__ float eval_candidates(const GraphView &g, const float *q, int32_t nb, unsigned mask,
+                                                 int lane)
+{
+    float myd = __int_as_float(0x7f800000);
+    unsigned rem = mask;
+#define HB_EVAL_GROUP(GG)                                                                          \
+    {                                                                                              \
+        int32_t ids[GG];                                                                           \
+        int src[GG];                                                                               \
+        _Pragma("unroll") for (int c = 0; c < GG; c++)                                             \
+        {                                                                                          \
+            src[c] = __ffs(rem) - 1;                                                               \
+            rem &= rem - 1;                                                                        \
+            ids[c] = __shfl_sync(FULL, nb, src[c]);                                                \
+        }                                                                                          \
+        const float s = group_distance<T, IP, NV, false, GG>(g.vecs, g.row_bytes, g.nvec, q, ids, lane); \
+        _Pragma("unroll") for (int c = 0; c < GG; c++)                                             \
+        {                                                                                          \
+            const float v = __shfl_sync(FULL, s, c * (32 / GG));                                   \
+            if (lane == src[c]) myd = v;                                                           \
+        }                                                                                          \
+    }
+    if constexpr (G >= 8) while (__popc(rem) >= 8) HB_EVAL_GROUP(8)
+    if constexpr (G >= 4) while (__popc(rem) >= 4) HB_EVAL_GROUP(4)
+    if constexpr (G >= 2) while (__popc(rem) >= 2) HB_EVAL_GROUP(2)
+    while (rem) HB_EVAL_GROUP(1)
+#undef HB_EVAL_GROUP
+    return myd;
+}
+
+// HnswSearchLayer.  Precondition: w holds the entry candidates (sorted, unexpanded) and vs holds
+// exactly their ids.  Postcondition: w[0 .. min(L, ef)) = the result, nearest first.
+template <typename T, bool IP, int NV, int G, typename VS>
+__device__ __forceinline__ int search_layer(const GraphView &g, WList &w, VS &vs, const float *q, int ef, int lc,
+                                            int lane, QueryCounters &ctr)
+{
+    const int deg = lc == 0 ? 2 * g.m : g.m;
+    int low = 0;
+    for (;;) {
+        int idx = -1;
+        for (int base = low; base < w.L; base += 32) {
+            const int i = base + lane;
+            const bool un = i < w.L && !(w.id[i] & EXP_BIT);
+            const unsigned b = __ballot_sync(FULL, un);
+            if (b) { idx = base + __ffs(b) - 1; break; }
+        }
+        if (idx < 0) break;
+        const uint32_t cid = w.id[idx];
+        __syncwarp();
+        if (lane == 0) w.id[idx] = cid | EXP_BIT;
+        __syncwarp();
+        low = idx + 1;
+        if (lc == 0) ctr.n_hop0++; else ctr.n_hopu++;
+        if (!vs.room(deg)) return ST_TABLE;
+        const int32_t *list = lc == 0 ? g.nbr0 + (size_t) cid * deg
+                                      : g.nbru + ((size_t) g.uoff[cid] + (lc - 1)) * g.m;
+        for (int cb = 0; cb < deg; cb += 32) {
+            const int i = cb + lane;
+            const int32_t nb = i < deg ? list[i] : -1;
+            bool isnew = false;
+            if (nb >= 0) isnew = vs.insert((uint32_t) nb);
+            const unsigned nmask = __ballot_sync(FULL, isnew);
+            if (nmask == 0) continue;
+            vs.count += __popc(nmask);
+            ctr.n_dist += __popc(nmask);
+            const float myd = eval_candidates<T, IP, NV, G>(g, q, nb, nmask, lane);
+            const bool full = w.L >= ef;
+            const float f = full ? w.d[ef - 1] : 0.f;
+            unsigned amask = __ballot_sync(FULL, isnew && (!full || myd < f));
+            while (amask) {
+                const int s = __ffs(amask) - 1;
+                amask &= amask - 1;
+                const float ed = __shfl_sync(FULL, myd, s);
+                const uint32_t eid = (uint32_t) __shfl_sync(FULL, nb, s);
+                if (w.L >= ef && !(ed < w.d[ef - 1])) continue;
+                const int st = wlist_insert(w, ed, eid, ef, lane, low);
+                if (st) return st;
+            }
+        }
+    }
+    return ST_OK;
+}
+
+// distance of the single element `e` (warp-uniform) to the staged query
+template <typename T, bool IP, int NV>
+__device__ __forceinline__ float one_distance(const GraphView &g, const float *q, int32_t e, int lane)
+{
+    const int32_t ids[1] = { e };
+    return group_distance<T, IP, NV, false, 1>(g.vecs, g.row_bytes, g.nvec, q, ids, lane);
+}
+
+}   // namespace hb

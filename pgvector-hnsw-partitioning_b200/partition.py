@@ -1,0 +1,116 @@
+"""Hash-partitioned HNSW: the fork's partition routing and fan-out/merge for the hot path.
+
+The reference mount has no source (/root/reference/README.md:1), so the partitioning contract is
+the one BASELINE.json states: a row goes to partition splitmix64(heap_tid) mod P; a query is
+broadcast to every partition; per-partition top-k lists are merged.  One process per GPU: rank r
+owns partitions {p : p mod world == r}; the only collective on the data path is one all-gather of
+nq x k (tid, distance) pairs per rank (NCCL over NVLink when the tensors are CUDA tensors).
+
+torch is used for device buffers, streams and torch.distributed only.
+"""
+import numpy as np
+
+from .hnsw import HB_F32, OPCLASSES, HnswError, HnswIndex, merge_topk_dev, partition_route
+
+
+def owned_partitions(n_partitions, rank, world):
+    return [p for p in range(n_partitions) if p % world == rank]
+
+
+class PartitionedIndex:
+    def __init__(self, dim, opclass="vector_l2_ops", n_partitions=8, m=16, ef_construction=64,
+                 capacity_per_partition=1 << 20, rank=0, world=1, device=0, seed=0, group=None):
+        if n_partitions < 1 or n_partitions > 64:
+            raise HnswError("n_partitions must be in [1, 64]")
+        self.dim, self.opclass, self.P, self.rank, self.world, self.device = dim, opclass, n_partitions, rank, world, device
+        self.group = group
+        self.metric, self.dtype = OPCLASSES[opclass]
+        self.owned = owned_partitions(n_partitions, rank, world)
+        self.parts = {p: HnswIndex(dim, opclass, m, ef_construction, capacity_per_partition, device, seed + p)
+                      for p in self.owned}
+
+    def close(self):
+        for ix in self.parts.values():
+            ix.close()
+        self.parts = {}
+
+    # ---- build: route rows to partitions, each rank indexes the partitions it owns; no collective
+    def build(self, vecs, heap_tids=None):
+        n = vecs.shape[0]
+        tids = np.arange(n, dtype=np.int64) if heap_tids is None else np.ascontiguousarray(heap_tids, np.int64)
+        part = partition_route(tids, self.P)
+        total = 0
+        for p, ix in self.parts.items():
+            sel = np.nonzero(part == p)[0]
+            if len(sel):
+                total += ix.insert(vecs[sel], tids[sel])
+        return total
+
+    @property
+    def n_local(self):
+        return sum(ix.n for ix in self.parts.values())
+
+    # ---- search
+    def search_local_dev(self, q_dev, k, ef_search):
+        """q_dev: CUDA tensor nq x dim of the index dtype on this rank's GPU.  Returns this rank's
+        merged (tids, dist) CUDA tensors, nq x k."""
+        import torch
+        nq = q_dev.shape[0]
+        dev = q_dev.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        npart = len(self.parts)
+        tids = torch.full((max(npart, 1), nq, k), -1, dtype=torch.int64, device=dev)
+        dist = torch.full((max(npart, 1), nq, k), float("inf"), dtype=torch.float32, device=dev)
+        elem = torch.empty((nq, ef_search), dtype=torch.int32, device=dev)
+        edist = torch.empty((nq, ef_search), dtype=torch.float32, device=dev)
+        cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+        for i, ix in enumerate(self.parts.values()):
+            if ix.n == 0:
+                continue
+            ix.search_dev(q_dev.data_ptr(), nq, ef_search, elem.data_ptr(), edist.data_ptr(), cnt.data_ptr(), stream)
+            ix.elements_to_tids_dev(elem.data_ptr(), edist.data_ptr(), nq, ef_search, k, tids[i].data_ptr(),
+                                    dist[i].data_ptr(), stream)
+        if npart <= 1:
+            return tids[0], dist[0]
+        out_t = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        merge_topk_dev(self.device, tids.data_ptr(), dist.data_ptr(), npart, nq, k, out_t.data_ptr(), out_d.data_ptr(), stream)
+        return out_t, out_d
+
+    def exchange(self, local_tids, local_dist):
+        """The one collective: all-gather of every rank's nq x k list -> world x nq x k."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return local_tids[None], local_dist[None]
+        nq, k = local_tids.shape
+        all_t = torch.empty((self.world, nq, k), dtype=local_tids.dtype, device=local_tids.device)
+        all_d = torch.empty((self.world, nq, k), dtype=local_dist.dtype, device=local_dist.device)
+        dist.all_gather_into_tensor(all_t, local_tids.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(all_d, local_dist.contiguous(), group=self.group)
+        return all_t, all_d
+
+    def search_dev(self, q_dev, k=10, ef_search=40):
+        """Broadcast queries are assumed resident on every rank.  Returns merged nq x k CUDA tensors
+        (identical on every rank)."""
+        import torch
+        lt, ld = self.search_local_dev(q_dev, k, ef_search)
+        all_t, all_d = self.exchange(lt, ld)
+        if self.world == 1:
+            return lt, ld
+        nq = q_dev.shape[0]
+        out_t = torch.empty((nq, k), dtype=torch.int64, device=q_dev.device)
+        out_d = torch.empty((nq, k), dtype=torch.float32, device=q_dev.device)
+        stream = torch.cuda.current_stream(q_dev.device).cuda_stream
+        merge_topk_dev(self.device, all_t.data_ptr(), all_d.data_ptr(), self.world, nq, k, out_t.data_ptr(),
+                       out_d.data_ptr(), stream)
+        return out_t, out_d
+
+    def search(self, queries, k=10, ef_search=40):
+        """Host arrays in/out (H2D + D2H inside)."""
+        import torch
+        tdt = torch.float32 if self.dtype == HB_F32 else torch.float16
+        q = torch.as_tensor(np.ascontiguousarray(queries)).to(tdt)
+        q_dev = q.to("cuda:%d" % self.device, non_blocking=True)
+        t, d = self.search_dev(q_dev, k, ef_search)
+        return t.cpu().numpy(), d.cpu().numpy()

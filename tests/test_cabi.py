@@ -1,0 +1,64 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/hnsw_b200.h
+declares; compute entry points fail loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, has_gpu
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "hnsw_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(pkg):
+    lib = ctypes.CDLL(pkg.lib_path())
+    names = declared_symbols()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(lib, name), "libhnsw_b200.so does not export %s" % name
+
+
+def test_binding_covers_header(pkg):
+    from pgvector_hnsw_partitioning_b200 import hnsw
+    assert set(declared_symbols()) <= set(hnsw._SIGS), set(declared_symbols()) - set(hnsw._SIGS)
+
+
+def test_opclass_surface(pkg):
+    assert set(pkg.OPCLASSES) == {"vector_l2_ops", "vector_ip_ops", "vector_cosine_ops",
+                                  "halfvec_l2_ops", "halfvec_ip_ops", "halfvec_cosine_ops"}
+    with pytest.raises(pkg.HnswError):
+        pkg.HnswIndex(8, "vector_l1_ops")
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-device failure mode")
+def test_no_cpu_fallback(pkg):
+    with pytest.raises(pkg.HnswError) as ei:
+        pkg.HnswIndex(8, "vector_l2_ops")
+    assert "CUDA" in str(ei.value) or "device" in str(ei.value)
+
+
+def test_partition_routing_matches_oracle(pkg, oracle):
+    ids = np.arange(-5, 5000, dtype=np.int64)
+    for P in (1, 2, 8, 13):
+        got = pkg.partition_route(ids, P)
+        want = np.array([oracle.splitmix64(int(i)) % P for i in ids], np.int32)
+        assert (got == want).all()
+        assert got.min() >= 0 and got.max() < P
+    # roughly uniform
+    cnt = np.bincount(pkg.partition_route(np.arange(80000), 8), minlength=8)
+    assert cnt.min() > 9000 and cnt.max() < 11000
+
+
+def test_level_draw_matches_oracle(pkg, oracle):
+    L = pkg.load_library()
+    L.hb_level_for.restype = ctypes.c_int
+    L.hb_level_for.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int]
+    for m in (4, 16, 48):
+        for i in range(3000):
+            assert L.hb_level_for(99, i, m) == oracle.level_for(99, i, m)
