@@ -405,7 +405,8 @@ int64_t hb_insert(hb_index *ix, const void *host_vecs, int64_t n, const int64_t 
 static int choose_slots(const hb_index *ix, int ef, int capW)
 {
     int slots = ix->opt_slots > 0 ? pow2ceil(ix->opt_slots) : pow2ceil(ef * 32);
-    if (slots < 1024) slots = 1024;
+    if (ix->opt_slots <= 0 && slots < 1024) slots = 1024;
+    if (slots < 64) slots = 64;
     // keep SCAN_WARPS warps within 200 kB of shared memory
     const size_t fixed = (size_t) ix->nvec * (ix->dtype == HB_F32 ? 4 : 8) * 4 + (size_t) capW * 8 + 16;
     while (slots > 256 && (fixed + (size_t) slots * 4) * SCAN_WARPS > 200 * 1024) slots >>= 1;

@@ -1,0 +1,518 @@
+// build_kernel.cuh -- the index-build hot path, batched.
+//
+// Roles [RECALL; the reference mount has no source, /root/reference/README.md:1]:
+//   build_search_kernel   <- hnswutils.c HnswFindElementNeighbors, search part: greedy descent then
+//                            HnswSearchLayer(ef_construction) per layer, for a whole batch of new
+//                            elements against the graph as it stood before the batch
+//   build_select_kernel   <- hnswutils.c SelectNeighbors + CheckElementCloser (heuristic with pruned
+//                            back-fill) and hnswbuild.c FindDuplicateInMemory
+//   build_commit_kernel   <- hnswutils.c AddConnections
+//   build_link_kernel     <- hnswutils.c HnswUpdateConnection (reverse links; re-selection when the
+//                            neighbour's list is full), one warp per (target, layer), edges applied in
+//                            source-id order
+// A batch is what pgvector's parallel build workers are to each other: elements inserted
+// concurrently do not see one another.
+#pragma once
+#include "search_core.cuh"
+#include <cuda_runtime.h>
+
+namespace hb {
+
+constexpr int BUILD_WARPS = 4;
+constexpr int DUP_SLOTS = 8;
+
+struct BuildSearchParams {
+    GraphView g;                 // the graph before the batch
+    int64_t first;               // new element i lives in row first + i
+    int B;
+    const uint8_t *level;        // B
+    const int32_t *ucand_row;    // B: first upper candidate row of element i (layers 1..), or -1
+    int efc, slots, upper_slots, capW;
+    int32_t *cand0_id; float *cand0_d; int32_t *cand0_cnt;   // B x efc, nearest first
+    int32_t *candu_id; float *candu_d; int32_t *candu_cnt;   // UR x efc
+    int32_t *status, *slow_list, *slow_count;
+    const int32_t *qlist, *qcount;
+    unsigned long long *totals;
+    unsigned int *work;
+    uint32_t *gbits; int gwords;
+    float *gwd; uint32_t *gwi; int gcap;
+};
+
+template <typename T> __host__ __device__ inline size_t build_warp_smem(int nvec, int capW, int slots, bool slow)
+{
+    size_t b = (size_t) nvec * Vec<T>::VEC * 4;
+    if (!slow) b += (size_t) capW * 8 + (size_t) slots * 4;
+    return (b + 15) & ~(size_t) 15;
+}
+
+template <typename T, bool IP, int NV, int G, bool SLOW>
+__global__ void __launch_bounds__(BUILD_WARPS * 32) build_search_kernel(const BuildSearchParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const GraphView &g = p.g;
+    unsigned char *base = smem + build_warp_smem<T>(g.nvec, p.capW, p.slots, SLOW) * warp;
+    float *q = reinterpret_cast<float *>(base);
+    using VS = typename std::conditional<SLOW, VisitedBitmap, VisitedHash>::type;
+    WList w;
+    VS vs;
+    if constexpr (SLOW) {
+        const size_t gw = (size_t) blockIdx.x * BUILD_WARPS + warp;
+        vs.bits = p.gbits + gw * p.gwords;
+        vs.words = p.gwords;
+        w.d = p.gwd + gw * p.gcap;
+        w.id = p.gwi + gw * p.gcap;
+        w.cap = p.gcap;
+    } else {
+        unsigned char *s = base + (size_t) g.nvec * Vec<T>::VEC * 4;
+        vs.tab = reinterpret_cast<uint32_t *>(s);
+        w.d = reinterpret_cast<float *>(s + (size_t) p.slots * 4);
+        w.id = reinterpret_cast<uint32_t *>(s + (size_t) p.slots * 4 + (size_t) p.capW * 4);
+        w.cap = p.capW;
+    }
+    const unsigned total = p.qlist ? (unsigned) *p.qcount : (unsigned) p.B;
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(p.work, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= total) break;
+        const int i = p.qlist ? p.qlist[item] : (int) item;
+        __syncwarp();
+        stage_query<T>(reinterpret_cast<const T *>(g.vecs + (size_t) (p.first + i) * g.row_bytes), g.dim, g.nvec, q, lane);
+        __syncwarp();
+
+        QueryCounters ctr = { 0, 0, 0 };
+        int st = ST_OK;
+        int level = p.level[i];
+        const float d0 = one_distance<T, IP, NV>(g, q, g.entry, lane);
+        ctr.n_dist = 1;
+        w.L = 1;
+        if (lane == 0) { w.d[0] = d0; w.id[0] = (uint32_t) g.entry; }
+        __syncwarp();
+        // 1st phase: greedy search to the insert level
+        vs.configure(p.upper_slots);
+        for (int lc = g.entry_level; lc >= level + 1 && st == ST_OK; lc--) {
+            wlist_as_entries(w, vs, 1, lane);
+            st = search_layer<T, IP, NV, G>(g, w, vs, q, 1, lc, lane, ctr);
+        }
+        if (level > g.entry_level) level = g.entry_level;
+        // 2nd phase: ef_construction candidates per layer; the whole result is the next entry list
+        vs.configure(p.slots);
+        int keep = 1;
+        for (int lc = level; lc >= 0 && st == ST_OK; lc--) {
+            wlist_as_entries(w, vs, keep, lane);
+            st = search_layer<T, IP, NV, G>(g, w, vs, q, p.efc, lc, lane, ctr);
+            if (st != ST_OK) break;
+            keep = p.efc;
+            const int cnt = min(w.L, p.efc);
+            int32_t *cid; float *cd;
+            if (lc == 0) {
+                cid = p.cand0_id + (size_t) i * p.efc; cd = p.cand0_d + (size_t) i * p.efc;
+                if (lane == 0) p.cand0_cnt[i] = cnt;
+            } else {
+                const size_t row = (size_t) p.ucand_row[i] + (lc - 1);
+                cid = p.candu_id + row * p.efc; cd = p.candu_d + row * p.efc;
+                if (lane == 0) p.candu_cnt[row] = cnt;
+            }
+            for (int j = lane; j < cnt; j += 32) { cid[j] = (int32_t) (w.id[j] & ID_MASK); cd[j] = w.d[j]; }
+        }
+        if (st != ST_OK && !SLOW) {
+            if (lane == 0) {
+                const int slot = atomicAdd(p.slow_count, 1);
+                p.slow_list[slot] = i;
+                p.status[i] = st;
+            }
+            continue;
+        }
+        if (lane == 0) {
+            p.status[i] = st == ST_OK ? 0 : -st;
+            atomicAdd(p.totals + 0, (unsigned long long) ctr.n_dist);
+            atomicAdd(p.totals + 1, (unsigned long long) ctr.n_hop0);
+            atomicAdd(p.totals + 2, (unsigned long long) ctr.n_hopu);
+            if (SLOW) atomicAdd(p.totals + 3, 1ull);
+        }
+    }
+}
+
+// ---- SelectNeighbors ------------------------------------------------------------------------
+// cand_*: candidates nearest first (key order) in shared memory.  r_*: the selected list in
+// upstream's list order (furthest-first when nc <= lm, else selection order then back-fill).
+// `pruned` = the candidate upstream reports as pruned (-1 when nothing was dropped).
+template <typename T, bool IP, int NV, int G>
+__device__ __forceinline__ int select_neighbors_warp(const GraphView &g, float *q, const int32_t *cand_id,
+                                                     const float *cand_d, int nc, int lm, int32_t *r_id, float *r_d,
+                                                     int32_t *wd_id, float *wd_d, int32_t &pruned, int lane,
+                                                     unsigned long long &npair)
+{
+    pruned = -1;
+    if (nc <= lm) {
+        for (int j = lane; j < nc; j += 32) { r_id[j] = cand_id[nc - 1 - j]; r_d[j] = cand_d[nc - 1 - j]; }
+        __syncwarp();
+        return nc;
+    }
+    int nr = 0, nwd = 0, i = 0;
+    while (i < nc && nr < lm) {
+        const int32_t e = cand_id[i];
+        const float ed = cand_d[i];
+        i++;
+        bool closer = true;
+        if (nr > 0) {
+            __syncwarp();
+            stage_query<T>(reinterpret_cast<const T *>(g.vecs + (size_t) e * g.row_bytes), g.dim, g.nvec, q, lane);
+            __syncwarp();
+            // CheckElementCloser: rejected as soon as one selected neighbour is at least as close
+            // to e as the owner is; evaluated eight selected neighbours at a time
+            for (int jb = 0; jb < nr && closer; jb += 8) {
+                const int j = jb + lane;
+                const int32_t nb = (lane < 8 && j < nr) ? r_id[j] : -1;
+                const unsigned mask = __ballot_sync(FULL, nb >= 0);
+                npair += __popc(mask);
+                const float d = eval_candidates<T, IP, NV, G>(g, q, nb, mask, lane);
+                if (__ballot_sync(FULL, nb >= 0 && d <= ed)) closer = false;
+            }
+        }
+        if (lane == 0) {
+            if (closer) { r_id[nr] = e; r_d[nr] = ed; }
+            else { wd_id[nwd] = e; wd_d[nwd] = ed; }
+        }
+        if (closer) nr++; else nwd++;
+        __syncwarp();
+    }
+    int wdoff = 0;
+    while (wdoff < nwd && nr < lm) {
+        if (lane == 0) { r_id[nr] = wd_id[wdoff]; r_d[nr] = wd_d[wdoff]; }
+        nr++; wdoff++;
+    }
+    __syncwarp();
+    pruned = wdoff < nwd ? wd_id[wdoff] : cand_id[nc - 1];
+    return nr;
+}
+
+struct BuildSelectParams {
+    GraphView g;
+    int64_t first;
+    int B, UR, efc;
+    const int32_t *cand0_id; const float *cand0_d; const int32_t *cand0_cnt;
+    const int32_t *candu_id; const float *candu_d; const int32_t *candu_cnt;
+    int32_t *sel0_id; float *sel0_d; int32_t *sel0_cnt;     // B x 2m
+    int32_t *selu_id; float *selu_d; int32_t *selu_cnt;     // UR x m
+    int32_t *dup;                                           // B x DUP_SLOTS: leading byte-identical neighbours
+    unsigned long long *totals;
+};
+
+template <typename T> __host__ __device__ inline size_t select_warp_smem(int nvec, int nc_max, int lm_max)
+{
+    size_t b = (size_t) nvec * Vec<T>::VEC * 4 + (size_t) nc_max * 16 + (size_t) lm_max * 8;
+    return (b + 15) & ~(size_t) 15;
+}
+
+template <typename T, bool IP, int NV, int G>
+__global__ void __launch_bounds__(BUILD_WARPS * 32) build_select_kernel(const BuildSelectParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const GraphView &g = p.g;
+    const int lm0 = 2 * g.m;
+    unsigned char *base = smem + select_warp_smem<T>(g.nvec, p.efc, lm0) * warp;
+    float *q = reinterpret_cast<float *>(base);
+    int32_t *c_id = reinterpret_cast<int32_t *>(base + (size_t) g.nvec * Vec<T>::VEC * 4);
+    float *c_d = reinterpret_cast<float *>(c_id + p.efc);
+    int32_t *wd_id = reinterpret_cast<int32_t *>(c_d + p.efc);
+    float *wd_d = reinterpret_cast<float *>(wd_id + p.efc);
+    int32_t *r_id = reinterpret_cast<int32_t *>(wd_d + p.efc);
+    float *r_d = reinterpret_cast<float *>(r_id + lm0);
+
+    const int items = p.B + p.UR;
+    unsigned long long npair = 0;
+    for (int item = blockIdx.x * BUILD_WARPS + warp; item < items; item += gridDim.x * BUILD_WARPS) {
+        const bool base_layer = item < p.B;
+        const int row = base_layer ? item : item - p.B;
+        const int nc = base_layer ? p.cand0_cnt[row] : p.candu_cnt[row];
+        const int32_t *gid = (base_layer ? p.cand0_id : p.candu_id) + (size_t) row * p.efc;
+        const float *gd = (base_layer ? p.cand0_d : p.candu_d) + (size_t) row * p.efc;
+        const int lm = base_layer ? lm0 : g.m;
+        __syncwarp();
+        for (int j = lane; j < nc; j += 32) { c_id[j] = gid[j]; c_d[j] = gd[j]; }
+        __syncwarp();
+        int32_t pruned;
+        const int nr = select_neighbors_warp<T, IP, NV, G>(g, q, c_id, c_d, nc, lm, r_id, r_d, wd_id, wd_d, pruned, lane, npair);
+        int32_t *oid = (base_layer ? p.sel0_id : p.selu_id) + (size_t) row * lm;
+        float *od = (base_layer ? p.sel0_d : p.selu_d) + (size_t) row * lm;
+        for (int j = lane; j < lm; j += 32) { oid[j] = j < nr ? r_id[j] : -1; od[j] = j < nr ? r_d[j] : 0.f; }
+        if (lane == 0) (base_layer ? p.sel0_cnt : p.selu_cnt)[row] = nr;
+        if (base_layer) {
+            // FindDuplicateInMemory: neighbours in stored order while byte-identical to the new row
+            const uint4 *mine = reinterpret_cast<const uint4 *>(g.vecs + (size_t) (p.first + row) * g.row_bytes);
+            int nd = 0;
+            for (int j = 0; j < nr && nd < DUP_SLOTS; j++) {
+                const uint4 *other = reinterpret_cast<const uint4 *>(g.vecs + (size_t) r_id[j] * g.row_bytes);
+                bool same = true;
+                for (int ch = lane; ch < g.nvec; ch += 32) {
+                    const uint4 a = mine[ch], b = other[ch];
+                    same = same && a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w;
+                }
+                if (!__all_sync(FULL, same)) break;
+                if (lane == 0) p.dup[(size_t) row * DUP_SLOTS + nd] = r_id[j];
+                nd++;
+            }
+            if (lane == 0 && nd < DUP_SLOTS) p.dup[(size_t) row * DUP_SLOTS + nd] = -1;
+        }
+    }
+    if (lane == 0 && npair) atomicAdd(p.totals + 4, npair);
+}
+
+// ---- AddConnections: write the selected lists of the surviving new elements -------------------
+struct BuildCommitParams {
+    int B, UR, m;
+    const int32_t *final_id;      // B: element id, or -1 for a tuple folded into a duplicate
+    const int32_t *dest_urow;     // UR: row in nbru, or -1
+    const int32_t *sel0_id; const float *sel0_d;
+    const int32_t *selu_id; const float *selu_d;
+    int32_t *nbr0; float *nbr0d; int32_t *nbru; float *nbrud;
+};
+
+__global__ void build_commit_kernel(const BuildCommitParams p)
+{
+    const int lm0 = 2 * p.m;
+    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n0 = (int64_t) p.B * lm0;
+    if (t < n0) {
+        const int i = (int) (t / lm0), j = (int) (t % lm0);
+        const int32_t f = p.final_id[i];
+        if (f >= 0) { p.nbr0[(size_t) f * lm0 + j] = p.sel0_id[t]; p.nbr0d[(size_t) f * lm0 + j] = p.sel0_d[t]; }
+    } else if (t < n0 + (int64_t) p.UR * p.m) {
+        const int64_t u = t - n0;
+        const int r = (int) (u / p.m), j = (int) (u % p.m);
+        const int32_t dr = p.dest_urow[r];
+        if (dr >= 0) { p.nbru[(size_t) dr * p.m + j] = p.selu_id[u]; p.nbrud[(size_t) dr * p.m + j] = p.selu_d[u]; }
+    }
+}
+
+// ---- HnswUpdateConnection -------------------------------------------------------------------
+struct BuildLinkParams {
+    GraphView g;
+    int S;                         // segments = distinct (target, layer) pairs
+    const int32_t *seg_off;        // S + 1
+    const int32_t *seg_target;     // S
+    const int32_t *seg_layer;      // S
+    const int32_t *edge_src;       // E, ascending source id within a segment
+    const float *edge_d;           // E
+    int32_t *nbr0; float *nbr0d; int32_t *nbru; float *nbrud;
+    unsigned long long *totals;
+};
+
+template <typename T, bool IP, int NV, int G>
+__global__ void __launch_bounds__(BUILD_WARPS * 32) build_link_kernel(const BuildLinkParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const GraphView &g = p.g;
+    const int lm0 = 2 * g.m, cap = lm0 + 1;
+    // per warp: query, list (id,d) x cap, sorted (id,d) x cap, wd (id,d) x cap, r (id,d) x lm0
+    unsigned char *base = smem + select_warp_smem<T>(g.nvec, 3 * cap / 2 + 2, lm0) * warp;
+    float *q = reinterpret_cast<float *>(base);
+    int32_t *l_id = reinterpret_cast<int32_t *>(base + (size_t) g.nvec * Vec<T>::VEC * 4);
+    float *l_d = reinterpret_cast<float *>(l_id + cap);
+    int32_t *s_id = reinterpret_cast<int32_t *>(l_d + cap);
+    float *s_d = reinterpret_cast<float *>(s_id + cap);
+    int32_t *wd_id = reinterpret_cast<int32_t *>(s_d + cap);
+    float *wd_d = reinterpret_cast<float *>(wd_id + cap);
+    int32_t *r_id = reinterpret_cast<int32_t *>(wd_d + cap);
+    float *r_d = reinterpret_cast<float *>(r_id + lm0);
+
+    unsigned long long npair = 0;
+    for (int seg = blockIdx.x * BUILD_WARPS + warp; seg < p.S; seg += gridDim.x * BUILD_WARPS) {
+        const int32_t target = p.seg_target[seg];
+        const int lc = p.seg_layer[seg];
+        const int lm = lc == 0 ? lm0 : g.m;
+        int32_t *gl;
+        float *gld;
+        if (lc == 0) { gl = p.nbr0 + (size_t) target * lm0; gld = p.nbr0d + (size_t) target * lm0; }
+        else {
+            const size_t row = (size_t) g.uoff[target] + (lc - 1);
+            gl = p.nbru + row * g.m; gld = p.nbrud + row * g.m;
+        }
+        __syncwarp();
+        int cnt = 0;
+        for (int jb = 0; jb < lm; jb += 32) {
+            const int j = jb + lane;
+            int32_t v = -1;
+            if (j < lm) { v = gl[j]; l_id[j] = v; l_d[j] = gld[j]; }
+            cnt += __popc(__ballot_sync(FULL, v >= 0));
+        }
+        __syncwarp();
+        for (int e = p.seg_off[seg]; e < p.seg_off[seg + 1]; e++) {
+            const int32_t src = p.edge_src[e];
+            const float d = p.edge_d[e];
+            if (cnt < lm) {
+                if (lane == 0) { l_id[cnt] = src; l_d[cnt] = d; }
+                cnt++;
+                __syncwarp();
+                continue;
+            }
+            // shrink: candidates = list + new, sorted by (distance, id) [sortCandidates = true]
+            if (lane == 0) { l_id[lm] = src; l_d[lm] = d; }
+            __syncwarp();
+            const int nc = lm + 1;
+            for (int ib = 0; ib < nc; ib += 32) {
+                const int i = ib + lane;
+                if (i < nc) {
+                    const float di = l_d[i];
+                    const int32_t ii = l_id[i];
+                    int rank = 0;
+                    for (int j = 0; j < nc; j++) {
+                        const float dj = l_d[j];
+                        rank += (dj < di || (dj == di && l_id[j] < ii)) ? 1 : 0;
+                    }
+                    s_id[rank] = ii; s_d[rank] = di;
+                }
+            }
+            __syncwarp();
+            int32_t pruned;
+            select_neighbors_warp<T, IP, NV, G>(g, q, s_id, s_d, nc, lm, r_id, r_d, wd_id, wd_d, pruned, lane, npair);
+            // find and replace the pruned element (nothing happens when the new one is pruned)
+            for (int jb = 0; jb < lm; jb += 32) {
+                const int j = jb + lane;
+                if (j < lm && l_id[j] == pruned) { l_id[j] = src; l_d[j] = d; }
+            }
+            __syncwarp();
+        }
+        for (int j = lane; j < lm; j += 32) {
+            if (j < cnt) { gl[j] = l_id[j]; gld[j] = l_d[j]; }
+        }
+    }
+    if (lane == 0 && npair) atomicAdd(p.totals + 4, npair);
+}
+
+// cached owner->neighbour distances for a graph that was loaded rather than built here
+struct NbrDistParams {
+    GraphView g;
+    int64_t rows;                 // n (layer 0) or upper rows
+    int deg;
+    const int32_t *owner_of_row;  // upper table: owning element of each row; NULL = row index
+    const int32_t *nbr; float *nbrd;
+};
+
+template <typename T, bool IP>
+__global__ void __launch_bounds__(BUILD_WARPS * 32) nbr_dist_kernel(const NbrDistParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const GraphView &g = p.g;
+    float *q = reinterpret_cast<float *>(smem + build_warp_smem<T>(g.nvec, 0, 0, true) * warp);
+    for (int64_t row = (int64_t) blockIdx.x * BUILD_WARPS + warp; row < p.rows; row += (int64_t) gridDim.x * BUILD_WARPS) {
+        const int64_t owner = p.owner_of_row ? p.owner_of_row[row] : row;
+        __syncwarp();
+        stage_query<T>(reinterpret_cast<const T *>(g.vecs + (size_t) owner * g.row_bytes), g.dim, g.nvec, q, lane);
+        __syncwarp();
+        for (int jb = 0; jb < p.deg; jb += 32) {
+            const int j = jb + lane;
+            const int32_t nb = j < p.deg ? p.nbr[row * p.deg + j] : -1;
+            const unsigned mask = __ballot_sync(FULL, nb >= 0);
+            const float d = eval_candidates<T, IP, 0, 2>(g, q, nb, mask, lane);
+            if (j < p.deg) p.nbrd[row * p.deg + j] = nb >= 0 ? d : 0.f;
+        }
+    }
+}
+
+// ---- launch helpers ---------------------------------------------------------------------------
+#define HB_NV_DISPATCH(nvec, CALL)                                                                 \
+    switch (((nvec) + 31) / 32) {                                                                  \
+    case 1: CALL(1, 8); break;                                                                     \
+    case 2: CALL(2, 8); break;                                                                     \
+    case 3: case 4: CALL(4, 4); break;                                                             \
+    case 5: case 6: CALL(6, 4); break;                                                             \
+    case 7: case 8: CALL(8, 2); break;                                                             \
+    default: CALL(0, 2); break;                                                                    \
+    }
+
+template <typename T, bool IP, bool SLOW>
+cudaError_t launch_build_search_t(const BuildSearchParams &p, int num_sms, int slow_grid, cudaStream_t stream)
+{
+    cudaError_t err = cudaSuccess;
+#define HB_CALL(NVV, GG)                                                                           \
+    {                                                                                              \
+        auto kern = build_search_kernel<T, IP, SLOW ? 0 : NVV, SLOW ? 2 : GG, SLOW>;               \
+        const size_t smem = build_warp_smem<T>(p.g.nvec, p.capW, p.slots, SLOW) * BUILD_WARPS;     \
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+        if (err == cudaSuccess) {                                                                  \
+            int bps = 0;                                                                           \
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, BUILD_WARPS * 32, smem); \
+            if (err == cudaSuccess) {                                                              \
+                if (bps < 1) err = cudaErrorInvalidConfiguration;                                  \
+                else {                                                                             \
+                    int64_t want = SLOW ? slow_grid : (p.B + BUILD_WARPS - 1) / BUILD_WARPS;       \
+                    int grid = (int) (want < (int64_t) bps * num_sms ? want : (int64_t) bps * num_sms); \
+                    if (grid < 1) grid = 1;                                                        \
+                    kern<<<grid, BUILD_WARPS * 32, smem, stream>>>(p);                             \
+                    err = cudaGetLastError();                                                      \
+                }                                                                                  \
+            }                                                                                      \
+        }                                                                                          \
+    }
+    HB_NV_DISPATCH(p.g.nvec, HB_CALL)
+#undef HB_CALL
+    return err;
+}
+
+template <typename T, bool IP>
+cudaError_t launch_build_select_t(const BuildSelectParams &p, int num_sms, cudaStream_t stream)
+{
+    cudaError_t err = cudaSuccess;
+    const int items = p.B + p.UR;
+    if (items <= 0) return err;
+#define HB_CALL(NVV, GG)                                                                           \
+    {                                                                                              \
+        auto kern = build_select_kernel<T, IP, NVV, (GG > 4 ? 4 : GG)>;                            \
+        const size_t smem = select_warp_smem<T>(p.g.nvec, p.efc, 2 * p.g.m) * BUILD_WARPS;         \
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+        if (err == cudaSuccess) {                                                                  \
+            int grid = (items + BUILD_WARPS - 1) / BUILD_WARPS;                                    \
+            if (grid > num_sms * 8) grid = num_sms * 8;                                            \
+            kern<<<grid, BUILD_WARPS * 32, smem, stream>>>(p);                                     \
+            err = cudaGetLastError();                                                              \
+        }                                                                                          \
+    }
+    HB_NV_DISPATCH(p.g.nvec, HB_CALL)
+#undef HB_CALL
+    return err;
+}
+
+template <typename T, bool IP>
+cudaError_t launch_build_link_t(const BuildLinkParams &p, int num_sms, cudaStream_t stream)
+{
+    cudaError_t err = cudaSuccess;
+    if (p.S <= 0) return err;
+#define HB_CALL(NVV, GG)                                                                           \
+    {                                                                                              \
+        auto kern = build_link_kernel<T, IP, NVV, (GG > 4 ? 4 : GG)>;                              \
+        const int cap = 2 * p.g.m + 1;                                                             \
+        const size_t smem = select_warp_smem<T>(p.g.nvec, 3 * cap / 2 + 2, 2 * p.g.m) * BUILD_WARPS; \
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+        if (err == cudaSuccess) {                                                                  \
+            int grid = (p.S + BUILD_WARPS - 1) / BUILD_WARPS;                                      \
+            if (grid > num_sms * 8) grid = num_sms * 8;                                            \
+            kern<<<grid, BUILD_WARPS * 32, smem, stream>>>(p);                                     \
+            err = cudaGetLastError();                                                              \
+        }                                                                                          \
+    }
+    HB_NV_DISPATCH(p.g.nvec, HB_CALL)
+#undef HB_CALL
+    return err;
+}
+
+template <typename T, bool IP>
+cudaError_t launch_nbr_dist_t(const NbrDistParams &p, int num_sms, cudaStream_t stream)
+{
+    if (p.rows <= 0) return cudaSuccess;
+    auto kern = nbr_dist_kernel<T, IP>;
+    const size_t smem = build_warp_smem<T>(p.g.nvec, 0, 0, true) * BUILD_WARPS;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (err != cudaSuccess) return err;
+    int64_t grid = (p.rows + BUILD_WARPS - 1) / BUILD_WARPS;
+    if (grid > num_sms * 8) grid = num_sms * 8;
+    kern<<<(int) grid, BUILD_WARPS * 32, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}   // namespace hb

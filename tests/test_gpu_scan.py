@@ -51,7 +51,10 @@ def test_distance_kernel_bit_exact(oracle, pkg, dim, metric):
             want = oracle.distance(qi, xs[cand[i, j]], oracle.L2 if metric == 0 else oracle.IP, 0, oracle.CANON)
             assert got[i, j] == np.float32(want), (i, j, got[i, j], want)
             nat = oracle.distance(qi, xs[cand[i, j]], oracle.L2 if metric == 0 else oracle.IP, 0, oracle.NATURAL)
-            assert abs(got[i, j] - nat) <= 1e-5 * max(abs(nat), 1e-3) + 1e-6
+            # 1e-5 relative to the magnitude of the summed terms (an inner product can cancel)
+            a64, b64 = qi.astype(np.float64), xs[cand[i, j]].astype(np.float64)
+            scale = ((a64 - b64) ** 2).sum() if metric == 0 else np.abs(a64 * b64).sum()
+            assert abs(got[i, j] - nat) <= 1e-5 * scale
     ix.close()
 
 
