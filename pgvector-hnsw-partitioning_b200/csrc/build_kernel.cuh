@@ -271,7 +271,7 @@ struct BuildCommitParams {
     int32_t *nbr0; float *nbr0d; int32_t *nbru; float *nbrud;
 };
 
-__global__ void build_commit_kernel(const BuildCommitParams p)
+static __global__ void build_commit_kernel(const BuildCommitParams p)
 {
     const int lm0 = 2 * p.m;
     const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;

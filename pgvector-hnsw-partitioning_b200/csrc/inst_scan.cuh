@@ -15,3 +15,24 @@ cudaError_t HB_CAT(scan_slow_, HBI_NAME)(const ScanParams &p, int sms, int mg, c
 }
 cudaError_t HB_CAT(dist_, HBI_NAME)(const DistBatchParams &p, cudaStream_t s) { return launch_dist_t<HBI_T, HBI_IP>(p, s); }
 }   // namespace hb
+
+#include "build_kernel.cuh"
+namespace hb {
+cudaError_t HB_CAT(build_search_, HBI_NAME)(const BuildSearchParams &p, int sms, int slow_grid, cudaStream_t s, bool slow)
+{
+    return slow ? launch_build_search_t<HBI_T, HBI_IP, true>(p, sms, slow_grid, s)
+                : launch_build_search_t<HBI_T, HBI_IP, false>(p, sms, slow_grid, s);
+}
+cudaError_t HB_CAT(build_select_, HBI_NAME)(const BuildSelectParams &p, int sms, cudaStream_t s)
+{
+    return launch_build_select_t<HBI_T, HBI_IP>(p, sms, s);
+}
+cudaError_t HB_CAT(build_link_, HBI_NAME)(const BuildLinkParams &p, int sms, cudaStream_t s)
+{
+    return launch_build_link_t<HBI_T, HBI_IP>(p, sms, s);
+}
+cudaError_t HB_CAT(nbr_dist_, HBI_NAME)(const NbrDistParams &p, int sms, cudaStream_t s)
+{
+    return launch_nbr_dist_t<HBI_T, HBI_IP>(p, sms, s);
+}
+}   // namespace hb

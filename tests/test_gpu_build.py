@@ -1,0 +1,128 @@
+"""The GPU build path (hnswbuild / hnswinsert) against the oracle.
+
+With a batch size of 1 the pipeline is the sequential algorithm, so the graph must be IDENTICAL to
+the oracle's (every neighbour list, in order).  With real batches elements of one batch do not see
+each other (as pgvector's parallel build workers do not), so the criterion is north_star's:
+recall@10 within 0.5 pt of the oracle-built graph."""
+import numpy as np
+import pytest
+
+from conftest import clustered, sift_like
+
+pytestmark = pytest.mark.gpu
+
+OPC = {(0, 0): "vector_l2_ops", (1, 0): "vector_ip_ops", (2, 0): "vector_cosine_ops",
+       (0, 1): "halfvec_l2_ops", (1, 1): "halfvec_ip_ops", (2, 1): "halfvec_cosine_ops"}
+
+
+def graphs_equal(a, b):
+    assert a.n == b.n and a.entry == b.entry and a.upper_rows == b.upper_rows
+    assert (a.level == b.level).all()
+    assert (a.uoff == b.uoff).all()
+    assert (a.vecs.view(np.uint8) == b.vecs.view(np.uint8)).all()
+    bad = np.nonzero((a.nbr0 != b.nbr0).any(axis=1))[0]
+    assert len(bad) == 0, "layer-0 lists differ for %d elements, first %s" % (len(bad), bad[:5])
+    if a.upper_rows:
+        assert (a.nbru[:a.upper_rows] == b.nbru[:b.upper_rows]).all()
+    assert (a.ntids == b.ntids).all()
+    for e in range(a.n):
+        assert (a.tids[e, :a.ntids[e]] == b.tids[e, :b.ntids[e]]).all()
+
+
+@pytest.mark.parametrize("metric,dtype,dim,m", [(0, 0, 32, 8), (2, 0, 100, 16), (1, 0, 24, 8), (1, 1, 64, 8), (0, 0, 128, 16)])
+def test_sequential_build_is_identical_to_oracle(oracle, pkg, metric, dtype, dim, m):
+    n = 1500
+    x = sift_like(n, dim, seed=1) if (metric == 0 and dim == 128) else clustered(n, dim, 16, seed=dim, dtype=np.float16 if dtype else np.float32)
+    efc = max(2 * m, 32)
+    orc = oracle.Index(dim, m, efc, metric, dtype, oracle.CANON, seed=5)
+    orc.build(x)
+    ix = pkg.HnswIndex(dim, OPC[(metric, dtype)], m, efc, capacity=n, seed=5)
+    ix.set_option("build_batch", 1)
+    assert ix.build(x) == n
+    graphs_equal(orc.export(), ix.export_graph())
+    ix.close()
+
+
+def test_sequential_build_with_duplicates_and_zero_vectors(oracle, pkg):
+    x = clustered(600, 16, 4, seed=2)
+    x[100:140] = x[7]          # 40 copies: more than HNSW_HEAPTIDS, several elements
+    x[300] = 0
+    for metric in (0, 2):
+        orc = oracle.Index(16, 8, 32, metric, 0, oracle.CANON, seed=9)
+        orc.build(x)
+        ix = pkg.HnswIndex(16, OPC[(metric, 0)], 8, 32, capacity=600, seed=9)
+        ix.set_option("build_batch", 1)
+        got = ix.build(x)
+        assert got == (599 if metric == 2 else 600)
+        graphs_equal(orc.export(), ix.export_graph())
+        t, d, c = ix.search(x[7:8], 60, 100)
+        wt, wd = orc.search_tids(x[7], 100, 60)
+        assert list(t[0][:len(wt)]) == list(wt)
+        ix.close()
+
+
+def test_insert_into_loaded_graph(oracle, pkg):
+    """hnswinsert after the graph came from elsewhere: cached neighbour distances are recomputed."""
+    x = clustered(1200, 20, 8, seed=3)
+    orc = oracle.Index(20, 8, 32, 0, 0, oracle.CANON, seed=2)
+    orc.build(x[:1000])
+    ix = pkg.HnswIndex(20, "vector_l2_ops", 8, 32, capacity=1200, seed=2)
+    ix.load_graph(orc.export())
+    ix.set_option("build_batch", 1)
+    assert ix.insert(x[1000:], np.arange(1000, 1200)) == 200
+    for i in range(1000, 1200):
+        orc.insert(x[i], i)
+    graphs_equal(orc.export(), ix.export_graph())
+    ix.close()
+
+
+def recall(ids, gt):
+    return float(np.mean([len(set(ids[i]) & set(gt[i])) / gt.shape[1] for i in range(len(gt))]))
+
+
+@pytest.mark.parametrize("metric,dtype,dim", [(0, 0, 128), (2, 0, 96), (1, 1, 64)])
+def test_batched_build_recall_within_half_point(oracle, pkg, metric, dtype, dim):
+    n, nq = 20000, 500
+    dt = np.float16 if dtype else np.float32
+    x = sift_like(n, dim, seed=4) if metric == 0 else clustered(n, dim, 64, seed=4, dtype=dt)
+    q = sift_like(nq, dim, seed=5) if metric == 0 else clustered(nq, dim, 64, seed=5, dtype=dt)
+    orc = oracle.Index(dim, 16, 64, metric, dtype, oracle.CANON, seed=1)
+    orc.build(x)
+    gt, _ = orc.bruteforce(q, 10, threads=8)
+    oe, _, _, _ = orc.search_batch(q, 40, threads=8)
+    r_oracle = recall(oe[:, :10], gt)
+    ix = pkg.HnswIndex(dim, OPC[(metric, dtype)], 16, 64, capacity=n, seed=1)
+    assert ix.build(x) == n
+    ge, gd, _ = ix.search_elements(q, 40)
+    r_gpu = recall(ge[:, :10], gt)
+    assert r_gpu >= r_oracle - 0.005, (r_gpu, r_oracle)
+    # the GPU-built graph is a valid HNSW graph: oracle search on it gives the same ids
+    g = ix.export_graph()
+    assert ((g.nbr0 >= -1) & (g.nbr0 < n)).all() and not (g.nbr0 == np.arange(n)[:, None]).any()
+    orc2 = oracle.Index.from_graph(g)
+    oe2, od2, _, _ = orc2.search_batch(q, 40, threads=8)
+    assert (oe2 == ge).all() and (od2 == gd).all()
+    c = ix.counters()
+    assert c["n_pair"] > 0
+    ix.close()
+
+
+def test_build_is_deterministic(pkg):
+    x = clustered(5000, 48, 32, seed=6)
+    gs = []
+    for _ in range(2):
+        ix = pkg.HnswIndex(48, "vector_cosine_ops", 16, 64, capacity=5000, seed=3)
+        ix.build(x)
+        gs.append(ix.export_graph())
+        ix.close()
+    graphs_equal(gs[0], gs[1])
+
+
+def test_capacity_and_argument_errors(pkg):
+    ix = pkg.HnswIndex(8, "vector_l2_ops", 8, 32, capacity=10)
+    with pytest.raises(pkg.HnswError):
+        ix.build(clustered(11, 8, 2, seed=1))
+    ix.close()
+    for bad in (dict(m=1), dict(m=101), dict(ef_construction=3), dict(m=40, ef_construction=64)):
+        with pytest.raises(pkg.HnswError):
+            pkg.HnswIndex(8, "vector_l2_ops", capacity=10, **bad)
