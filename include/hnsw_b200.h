@@ -113,11 +113,19 @@ void hb_endscan(hb_scan *scan);
  * writes the first k heap TIDs nearest-first (pad: -1 / +inf) and the count. */
 int hb_search_batch(hb_index *ix, const void *host_queries, int64_t nq, int ef_search, int k,
                     int64_t *out_tids, float *out_dist, int32_t *out_cnt);
+/* asynchronous form: the H2D copy, scan, TID mapping and D2H copy are queued on the stream of
+ * `slot` (0..3) and the call returns; hb_search_batch_wait(slot) completes it.  Batches in
+ * different slots overlap (copies under scans, one batch's tail under the next one's ramp).  Host
+ * buffers must stay valid -- and be pinned for the copies to overlap -- until the wait. */
+int hb_search_batch_async(hb_index *ix, int slot, const void *host_queries, int64_t nq, int ef_search,
+                          int k, int64_t *out_tids, float *out_dist, int32_t *out_cnt);
+int hb_search_batch_wait(hb_index *ix, int slot);
 /* as above but returns elements (graph node ids), ef per query: out_elem/out_dist nq x ef */
 int hb_search_batch_elements(hb_index *ix, const void *host_queries, int64_t nq, int ef_search,
                              int32_t *out_elem, float *out_dist, int32_t *out_cnt);
 /* device-resident: queries already in HBM (nq x dim, index dtype), results left in HBM;
- * asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream).
+ * asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream).  Calls on
+ * different streams may be in flight together (each stream gets its own workspace).
  * dev_out_elem / dev_out_dist: nq x ef; dev_out_cnt: nq. */
 int hb_search_batch_dev(hb_index *ix, const void *dev_queries, int64_t nq, int ef_search,
                         int32_t *dev_out_elem, float *dev_out_dist, int32_t *dev_out_cnt,
@@ -139,6 +147,10 @@ float hb_last_search_ms(const hb_index *ix);
  * (cand nq x nc, ids < 0 give +inf).  The query-vs-neighbour-list kernel on its own. */
 int hb_distance_batch(hb_index *ix, const void *host_queries, int64_t nq, const int32_t *cand,
                       int nc, float *out_dist);
+/* device-resident form (queries nq x dim, cand nq x nc, out nq x nc all in HBM; queries must be
+ * normalised already under the cosine opclass); asynchronous on stream */
+int hb_distance_batch_dev(hb_index *ix, const void *dev_queries, int64_t nq, const int32_t *dev_cand,
+                          int nc, float *dev_out, void *stream);
 /* FUNCTION 2 + l2_normalize: n x dim in, n x dim out (index dtype), ok[i] = 0 for zero norm */
 int hb_normalize(hb_index *ix, const void *host_in, int64_t n, void *host_out, uint8_t *ok);
 

@@ -169,6 +169,7 @@ dist_launch_fn get_dist_launcher(int dtype, bool ip)
     return ip ? dist_f16_ip : dist_f16_l2;
 }
 
+constexpr int HB_OVERFLOW_SLOTS = 4096;
 static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 // upload n rows of dim components into the padded row layout
@@ -265,10 +266,12 @@ void hb_index_free(hb_index *ix)
     cudaFree(ix->d_vecs); cudaFree(ix->d_nbr0); cudaFree(ix->d_nbr0d); cudaFree(ix->d_uoff);
     cudaFree(ix->d_nbru); cudaFree(ix->d_nbrud); cudaFree(ix->d_tid0); cudaFree(ix->d_ntids);
     cudaFree(ix->d_tidx); cudaFree(ix->d_totals);
-    hb::DevBuf *bufs[] = { &ix->ws_q, &ix->ws_qn, &ix->ws_elem, &ix->ws_dist, &ix->ws_cnt, &ix->ws_status,
-                           &ix->ws_slow, &ix->ws_misc, &ix->ws_pq, &ix->ws_tids, &ix->ws_tdist,
-                           &ix->ws_gbits, &ix->ws_gwd, &ix->ws_gwi, &ix->ws_ep };
+    hb::DevBuf *bufs[] = { &ix->ws_q, &ix->ws_qn, &ix->ws_elem, &ix->ws_dist, &ix->ws_status, &ix->ws_misc,
+                           &ix->ws_gbits, &ix->ws_gwd, &ix->ws_gwi, &ix->ws_ovf };
     for (auto b : bufs) b->release();
+    for (auto &w : ix->slot_ws) if (w) { w->release(); delete w; w = nullptr; }
+    for (auto &kv : ix->stream_ws) { kv.second->release(); delete kv.second; }
+    ix->stream_ws.clear();
     for (auto &b : ix->ws_build) b.release();
     if (ix->ev0) cudaEventDestroy(ix->ev0);
     if (ix->ev1) cudaEventDestroy(ix->ev1);
@@ -294,6 +297,7 @@ int hb_set_option(hb_index *ix, const char *name, int value)
     else if (!strcmp(name, "grid")) ix->opt_grid = value;
     else if (!strcmp(name, "build_batch")) ix->opt_build_batch = value;
     else if (!strcmp(name, "per_query_counters")) ix->opt_per_query = value;
+    else if (!strcmp(name, "variant")) ix->opt_variant = value;
     else { set_error("hb_set_option: unknown option %s", name); return HB_EINVAL; }
     return HB_OK;
 }
@@ -404,7 +408,9 @@ int64_t hb_insert(hb_index *ix, const void *host_vecs, int64_t n, const int64_t 
 // ---- scan ------------------------------------------------------------------------------------
 static int choose_slots(const hb_index *ix, int ef, int capW)
 {
-    int slots = ix->opt_slots > 0 ? pow2ceil(ix->opt_slots) : pow2ceil(ef * 32);
+    // ~5-12 distance evaluations per unit of ef is typical; heavier queries spill into the per-warp
+    // overflow table in HBM
+    int slots = ix->opt_slots > 0 ? pow2ceil(ix->opt_slots) : pow2ceil(ef * 16);
     if (ix->opt_slots <= 0 && slots < 1024) slots = 1024;
     if (slots < 64) slots = 64;
     // keep SCAN_WARPS warps within 200 kB of shared memory
@@ -413,23 +419,46 @@ static int choose_slots(const hb_index *ix, int ef, int capW)
     return slots;
 }
 
+static ScanWs *ws_for_stream(hb_index *ix, cudaStream_t s)
+{
+    auto it = ix->stream_ws.find((void *) s);
+    if (it != ix->stream_ws.end()) return it->second;
+    ScanWs *ws = new ScanWs();
+    if (cudaEventCreate(&ws->ev0) != cudaSuccess || cudaEventCreate(&ws->ev1) != cudaSuccess ||
+        cudaMallocHost(&ws->h_err, 64) != cudaSuccess) { delete ws; return nullptr; }
+    ix->stream_ws[(void *) s] = ws;
+    return ws;
+}
+
+static ScanWs *ws_for_slot(hb_index *ix, int slot)
+{
+    if (slot < 0 || slot >= ASYNC_SLOTS) return nullptr;
+    if (ix->slot_ws[slot]) return ix->slot_ws[slot];
+    ScanWs *ws = new ScanWs();
+    if (cudaStreamCreateWithFlags(&ws->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ws->ev0) != cudaSuccess || cudaEventCreate(&ws->ev1) != cudaSuccess ||
+        cudaMallocHost(&ws->h_err, 64) != cudaSuccess) { delete ws; return nullptr; }
+    ix->slot_ws[slot] = ws;
+    return ws;
+}
+
 // normalise queries on the device when the opclass is cosine; returns the pointer to scan with
-static int prepare_queries(hb_index *ix, const void *dev_q, int64_t nq, cudaStream_t s, const void **out)
+static int prepare_queries(hb_index *ix, ScanWs &ws, const void *dev_q, int64_t nq, cudaStream_t s, const void **out)
 {
     if (ix->metric != HB_COSINE) { *out = dev_q; return HB_OK; }
-    HB_CK(ix->ws_qn.ensure((size_t) nq * ix->dim * ix->esize));
+    HB_CK(ws.qn.ensure((size_t) nq * ix->dim * ix->esize));
     const int wpb = 8;
     const int grid = (int) ((nq + wpb - 1) / wpb);
     if (ix->dtype == HB_F32)
-        normalize_kernel<float><<<grid, wpb * 32, 0, s>>>((const float *) dev_q, ix->ws_qn.as<float>(), nullptr, nq, ix->dim);
+        normalize_kernel<float><<<grid, wpb * 32, 0, s>>>((const float *) dev_q, ws.qn.as<float>(), nullptr, nq, ix->dim);
     else
-        normalize_kernel<__half><<<grid, wpb * 32, 0, s>>>((const __half *) dev_q, ix->ws_qn.as<__half>(), nullptr, nq, ix->dim);
+        normalize_kernel<__half><<<grid, wpb * 32, 0, s>>>((const __half *) dev_q, ws.qn.as<__half>(), nullptr, nq, ix->dim);
     HB_CK(cudaGetLastError());
-    *out = ix->ws_qn.p;
+    *out = ws.qn.p;
     return HB_OK;
 }
 
-static int scan_dev(hb_index *ix, const void *dev_queries, int64_t nq, int ef, int32_t *out_elem, float *out_dist,
+static int scan_dev(hb_index *ix, ScanWs &ws, const void *dev_queries, int64_t nq, int ef, int32_t *out_elem, float *out_dist,
                     int32_t *out_cnt, cudaStream_t s, const int32_t *dev_ep, int nep, int layer)
 {
     if (ef < 1 || ef > 1000) { set_error("hnsw.ef_search must be in [1,1000] (got %d)", ef); return HB_EINVAL; }
@@ -437,7 +466,7 @@ static int scan_dev(hb_index *ix, const void *dev_queries, int64_t nq, int ef, i
     if (nq > 0x7fffffff) { set_error("too many queries in one batch"); return HB_EINVAL; }
     HB_CK(cudaSetDevice(ix->device));
     const void *q = nullptr;
-    int rc = prepare_queries(ix, dev_queries, nq, s, &q);
+    int rc = prepare_queries(ix, ws, dev_queries, nq, s, &q);
     if (rc) return rc;
 
     ScanParams p;
@@ -452,18 +481,20 @@ static int scan_dev(hb_index *ix, const void *dev_queries, int64_t nq, int ef, i
     p.out_elem = out_elem; p.out_dist = out_dist; p.out_cnt = out_cnt;
     p.out_stride = std::max(ef, nep);
     p.ep = dev_ep; p.nep = nep; p.layer = layer;
+    p.variant = ix->opt_variant;
 
-    HB_CK(ix->ws_status.ensure(sizeof(int32_t) * nq));
-    HB_CK(ix->ws_slow.ensure(sizeof(int32_t) * nq));
-    HB_CK(ix->ws_misc.ensure(256));
-    p.status = ix->ws_status.as<int32_t>();
-    p.slow_list = ix->ws_slow.as<int32_t>();
-    unsigned int *misc = ix->ws_misc.as<unsigned int>();   // [0] work fast, [1] work slow, [2] slow_count
+    HB_CK(ws.status.ensure(sizeof(int32_t) * nq));
+    HB_CK(ws.slow.ensure(sizeof(int32_t) * nq));
+    HB_CK(ws.misc.ensure(256));
+    p.status = ws.status.as<int32_t>();
+    p.slow_list = ws.slow.as<int32_t>();
+    unsigned int *misc = ws.misc.as<unsigned int>();   // [0] work fast, [1] work slow, [2] slow_count
     p.slow_count = reinterpret_cast<int32_t *>(misc + 2);
+    p.err = reinterpret_cast<int32_t *>(misc + 3);
     p.totals = ix->d_totals;
     if (ix->opt_per_query) {
-        HB_CK(ix->ws_pq.ensure(sizeof(int32_t) * 4 * nq));
-        p.per_query = ix->ws_pq.as<int32_t>();
+        HB_CK(ws.pq.ensure(sizeof(int32_t) * 4 * nq));
+        p.per_query = ws.pq.as<int32_t>();
     }
     HB_CK(cudaMemsetAsync(misc, 0, 16, s));
 
@@ -472,39 +503,45 @@ static int scan_dev(hb_index *ix, const void *dev_queries, int64_t nq, int ef, i
     const int64_t slow_warps = (int64_t) slow_grid * SCAN_WARPS;
     p.gwords = (int) ((ix->n + 31) / 32 + 1);
     p.gcap = std::max(ef, nep) + HB_TIE_LIMIT;
-    HB_CK(ix->ws_gbits.ensure(sizeof(uint32_t) * slow_warps * p.gwords));
-    HB_CK(ix->ws_gwd.ensure(sizeof(float) * slow_warps * p.gcap));
-    HB_CK(ix->ws_gwi.ensure(sizeof(uint32_t) * slow_warps * p.gcap));
-    p.gbits = ix->ws_gbits.as<uint32_t>();
-    p.gwd = ix->ws_gwd.as<float>();
-    p.gwi = ix->ws_gwi.as<uint32_t>();
+    HB_CK(ws.gbits.ensure(sizeof(uint32_t) * slow_warps * p.gwords));
+    HB_CK(ws.gwd.ensure(sizeof(float) * slow_warps * p.gcap));
+    HB_CK(ws.gwi.ensure(sizeof(uint32_t) * slow_warps * p.gcap));
+    p.gbits = ws.gbits.as<uint32_t>();
+    p.gwd = ws.gwd.as<float>();
+    p.gwi = ws.gwi.as<uint32_t>();
+
+    // per-warp visited overflow tables for the fast path (one slice per resident warp; the launcher
+    // keeps at most MAX_CTAS_PER_SM CTAs per SM resident)
+    p.oslots = HB_OVERFLOW_SLOTS;
+    HB_CK(ws.ovf.ensure(sizeof(uint32_t) * (size_t) ix->num_sms * MAX_CTAS_PER_SM * SCAN_WARPS * p.oslots));
+    p.ovf = ws.ovf.as<uint32_t>();
 
     const bool ip = ix->metric != HB_L2;
-    HB_CK(cudaEventRecord(ix->ev0, s));
+    HB_CK(cudaEventRecord(ws.ev0, s));
     p.work = misc + 0;
     ScanLaunchInfo info;
     HB_CK(get_scan_launcher(ix->dtype, ip, false)(p, ix->num_sms, ix->opt_grid, s, &info));
-    // queries whose visited table or tie tail overflowed run again with a bitmap in HBM
+    // queries whose tie tail (or overflow table) outgrew the fast path run again with a bitmap in HBM
     ScanParams ps = p;
     ps.work = misc + 1;
     ps.qlist = p.slow_list;
     ps.qcount = p.slow_count;
     HB_CK(get_scan_launcher(ix->dtype, ip, true)(ps, ix->num_sms, slow_grid, s, nullptr));
-    HB_CK(cudaEventRecord(ix->ev1, s));
-    ix->timing_valid = true;
+    HB_CK(cudaEventRecord(ws.ev1, s));
+    ws.timing_valid = true;
+    ix->last_ws = &ws;
     return HB_OK;
 }
 
-static int check_status(hb_index *ix, int64_t nq, cudaStream_t s)
+static int check_status(hb_index *ix, ScanWs &ws, int64_t nq, cudaStream_t s)
 {
-    std::vector<int32_t> st(nq);
-    HB_CK(cudaMemcpyAsync(st.data(), ix->ws_status.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, s));
+    (void) ix; (void) nq;
+    HB_CK(cudaMemcpyAsync(ws.h_err, ws.misc.as<int32_t>() + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     HB_CK(cudaStreamSynchronize(s));
-    for (int64_t i = 0; i < nq; i++)
-        if (st[i] < 0) {
-            set_error("query %lld: more than %d candidates tie exactly at the ef boundary", (long long) i, HB_TIE_LIMIT);
-            return HB_ELIMIT;
-        }
+    if (*ws.h_err) {
+        set_error("a query has more than %d candidates tying exactly at the ef boundary", HB_TIE_LIMIT);
+        return HB_ELIMIT;
+    }
     return HB_OK;
 }
 
@@ -512,7 +549,9 @@ int hb_search_batch_dev(hb_index *ix, const void *dev_queries, int64_t nq, int e
                         float *dev_out_dist, int32_t *dev_out_cnt, void *stream)
 {
     if (!ix || !dev_queries || !dev_out_elem || !dev_out_dist || !dev_out_cnt) { set_error("hb_search_batch_dev: NULL argument"); return HB_EINVAL; }
-    return scan_dev(ix, dev_queries, nq, ef, dev_out_elem, dev_out_dist, dev_out_cnt, (cudaStream_t) stream, nullptr, 0, 0);
+    ScanWs *ws = ws_for_stream(ix, (cudaStream_t) stream);
+    if (!ws) { set_error("hb_search_batch_dev: cannot create the stream workspace"); return HB_ECUDA; }
+    return scan_dev(ix, *ws, dev_queries, nq, ef, dev_out_elem, dev_out_dist, dev_out_cnt, (cudaStream_t) stream, nullptr, 0, 0);
 }
 
 int hb_search_batch_elements(hb_index *ix, const void *host_queries, int64_t nq, int ef, int32_t *out_elem,
@@ -521,18 +560,21 @@ int hb_search_batch_elements(hb_index *ix, const void *host_queries, int64_t nq,
     if (!ix || !host_queries || !out_elem || !out_dist) { set_error("hb_search_batch_elements: NULL argument"); return HB_EINVAL; }
     if (nq <= 0) return HB_OK;
     HB_CK(cudaSetDevice(ix->device));
-    cudaStream_t s = ix->stream;
-    HB_CK(ix->ws_q.ensure((size_t) nq * ix->dim * ix->esize));
-    HB_CK(ix->ws_elem.ensure(sizeof(int32_t) * nq * ef));
-    HB_CK(ix->ws_dist.ensure(sizeof(float) * nq * ef));
-    HB_CK(ix->ws_cnt.ensure(sizeof(int32_t) * nq));
-    HB_CK(cudaMemcpyAsync(ix->ws_q.p, host_queries, (size_t) nq * ix->dim * ix->esize, cudaMemcpyHostToDevice, s));
-    int rc = scan_dev(ix, ix->ws_q.p, nq, ef, ix->ws_elem.as<int32_t>(), ix->ws_dist.as<float>(), ix->ws_cnt.as<int32_t>(), s, nullptr, 0, 0);
+    ScanWs *wsp = ws_for_slot(ix, 0);
+    if (!wsp) { set_error("cannot create the scan workspace"); return HB_ECUDA; }
+    ScanWs &ws = *wsp;
+    cudaStream_t s = ws.own_stream;
+    HB_CK(ws.q.ensure((size_t) nq * ix->dim * ix->esize));
+    HB_CK(ws.elem.ensure(sizeof(int32_t) * nq * ef));
+    HB_CK(ws.dist.ensure(sizeof(float) * nq * ef));
+    HB_CK(ws.cnt.ensure(sizeof(int32_t) * nq));
+    HB_CK(cudaMemcpyAsync(ws.q.p, host_queries, (size_t) nq * ix->dim * ix->esize, cudaMemcpyHostToDevice, s));
+    int rc = scan_dev(ix, ws, ws.q.p, nq, ef, ws.elem.as<int32_t>(), ws.dist.as<float>(), ws.cnt.as<int32_t>(), s, nullptr, 0, 0);
     if (rc) return rc;
-    HB_CK(cudaMemcpyAsync(out_elem, ix->ws_elem.p, sizeof(int32_t) * nq * ef, cudaMemcpyDeviceToHost, s));
-    HB_CK(cudaMemcpyAsync(out_dist, ix->ws_dist.p, sizeof(float) * nq * ef, cudaMemcpyDeviceToHost, s));
-    if (out_cnt) HB_CK(cudaMemcpyAsync(out_cnt, ix->ws_cnt.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, s));
-    return check_status(ix, nq, s);
+    HB_CK(cudaMemcpyAsync(out_elem, ws.elem.p, sizeof(int32_t) * nq * ef, cudaMemcpyDeviceToHost, s));
+    HB_CK(cudaMemcpyAsync(out_dist, ws.dist.p, sizeof(float) * nq * ef, cudaMemcpyDeviceToHost, s));
+    if (out_cnt) HB_CK(cudaMemcpyAsync(out_cnt, ws.cnt.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, s));
+    return check_status(ix, ws, nq, s);
 }
 
 int hb_elements_to_tids_dev(hb_index *ix, const int32_t *dev_elem, const float *dev_dist, int64_t nq, int ef, int k,
@@ -547,30 +589,64 @@ int hb_elements_to_tids_dev(hb_index *ix, const int32_t *dev_elem, const float *
     return HB_OK;
 }
 
+// host buffers in / out, asynchronous: H2D, scan, TID mapping and D2H are queued on the slot's own
+// stream; hb_search_batch_wait() completes the call.  Up to ASYNC_SLOTS batches can be in flight,
+// so copies of one batch overlap the scan of another and one batch's tail overlaps the next one's
+// ramp.  The host buffers must stay valid (and, to overlap, be pinned) until the wait.
+int hb_search_batch_async(hb_index *ix, int slot, const void *host_queries, int64_t nq, int ef, int k, int64_t *out_tids,
+                          float *out_dist, int32_t *out_cnt)
+{
+    if (!ix || !host_queries || !out_tids || !out_dist || k < 1) { set_error("hb_search_batch: bad argument"); return HB_EINVAL; }
+    HB_CK(cudaSetDevice(ix->device));
+    ScanWs *wsp = ws_for_slot(ix, slot);
+    if (!wsp) { set_error("hb_search_batch_async: bad slot %d (0..%d)", slot, ASYNC_SLOTS - 1); return HB_EINVAL; }
+    ScanWs &ws = *wsp;
+    if (ws.pending) { set_error("hb_search_batch_async: slot %d still has a batch in flight", slot); return HB_ESTATE; }
+    if (nq <= 0) return HB_OK;
+    cudaStream_t s = ws.own_stream;
+    HB_CK(ws.q.ensure((size_t) nq * ix->dim * ix->esize));
+    HB_CK(ws.elem.ensure(sizeof(int32_t) * nq * ef));
+    HB_CK(ws.dist.ensure(sizeof(float) * nq * ef));
+    HB_CK(ws.cnt.ensure(sizeof(int32_t) * nq));
+    HB_CK(ws.tids.ensure(sizeof(int64_t) * nq * k));
+    HB_CK(ws.tdist.ensure(sizeof(float) * nq * k));
+    HB_CK(cudaMemcpyAsync(ws.q.p, host_queries, (size_t) nq * ix->dim * ix->esize, cudaMemcpyHostToDevice, s));
+    int rc = scan_dev(ix, ws, ws.q.p, nq, ef, ws.elem.as<int32_t>(), ws.dist.as<float>(), ws.cnt.as<int32_t>(), s, nullptr, 0, 0);
+    if (rc) return rc;
+    elements_to_tids_kernel<<<(int) ((nq + 127) / 128), 128, 0, s>>>(ws.elem.as<int32_t>(), ws.dist.as<float>(), nq, ef, k,
+                                                                      ix->d_tid0, ix->d_ntids, ix->d_tidx, ws.tids.as<int64_t>(),
+                                                                      ws.tdist.as<float>(), ws.cnt.as<int32_t>());
+    HB_CK(cudaGetLastError());
+    HB_CK(cudaMemcpyAsync(out_tids, ws.tids.p, sizeof(int64_t) * nq * k, cudaMemcpyDeviceToHost, s));
+    HB_CK(cudaMemcpyAsync(out_dist, ws.tdist.p, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, s));
+    if (out_cnt) HB_CK(cudaMemcpyAsync(out_cnt, ws.cnt.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, s));
+    HB_CK(cudaMemcpyAsync(ws.h_err, ws.misc.as<int32_t>() + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    ws.pending = true;
+    ws.pending_nq = nq;
+    return HB_OK;
+}
+
+int hb_search_batch_wait(hb_index *ix, int slot)
+{
+    if (!ix || slot < 0 || slot >= ASYNC_SLOTS) { set_error("hb_search_batch_wait: bad argument"); return HB_EINVAL; }
+    ScanWs *wsp = ix->slot_ws[slot];
+    if (!wsp || !wsp->pending) return HB_OK;
+    HB_CK(cudaSetDevice(ix->device));
+    HB_CK(cudaStreamSynchronize(wsp->own_stream));
+    wsp->pending = false;
+    if (*wsp->h_err) {
+        set_error("a query has more than %d candidates tying exactly at the ef boundary", HB_TIE_LIMIT);
+        return HB_ELIMIT;
+    }
+    return HB_OK;
+}
+
 int hb_search_batch(hb_index *ix, const void *host_queries, int64_t nq, int ef, int k, int64_t *out_tids,
                     float *out_dist, int32_t *out_cnt)
 {
-    if (!ix || !host_queries || !out_tids || !out_dist || k < 1) { set_error("hb_search_batch: bad argument"); return HB_EINVAL; }
-    if (nq <= 0) return HB_OK;
-    HB_CK(cudaSetDevice(ix->device));
-    cudaStream_t s = ix->stream;
-    HB_CK(ix->ws_q.ensure((size_t) nq * ix->dim * ix->esize));
-    HB_CK(ix->ws_elem.ensure(sizeof(int32_t) * nq * ef));
-    HB_CK(ix->ws_dist.ensure(sizeof(float) * nq * ef));
-    HB_CK(ix->ws_cnt.ensure(sizeof(int32_t) * nq));
-    HB_CK(ix->ws_tids.ensure(sizeof(int64_t) * nq * k));
-    HB_CK(ix->ws_tdist.ensure(sizeof(float) * nq * k));
-    HB_CK(cudaMemcpyAsync(ix->ws_q.p, host_queries, (size_t) nq * ix->dim * ix->esize, cudaMemcpyHostToDevice, s));
-    int rc = scan_dev(ix, ix->ws_q.p, nq, ef, ix->ws_elem.as<int32_t>(), ix->ws_dist.as<float>(), ix->ws_cnt.as<int32_t>(), s, nullptr, 0, 0);
+    int rc = hb_search_batch_async(ix, 0, host_queries, nq, ef, k, out_tids, out_dist, out_cnt);
     if (rc) return rc;
-    elements_to_tids_kernel<<<(int) ((nq + 127) / 128), 128, 0, s>>>(ix->ws_elem.as<int32_t>(), ix->ws_dist.as<float>(), nq, ef, k,
-                                                                      ix->d_tid0, ix->d_ntids, ix->d_tidx, ix->ws_tids.as<int64_t>(),
-                                                                      ix->ws_tdist.as<float>(), ix->ws_cnt.as<int32_t>());
-    HB_CK(cudaGetLastError());
-    HB_CK(cudaMemcpyAsync(out_tids, ix->ws_tids.p, sizeof(int64_t) * nq * k, cudaMemcpyDeviceToHost, s));
-    HB_CK(cudaMemcpyAsync(out_dist, ix->ws_tdist.p, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, s));
-    if (out_cnt) HB_CK(cudaMemcpyAsync(out_cnt, ix->ws_cnt.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, s));
-    return check_status(ix, nq, s);
+    return hb_search_batch_wait(ix, 0);
 }
 
 int hb_search_layer(hb_index *ix, const void *host_queries, int64_t nq, const int32_t *ep, int nep, int ef, int layer,
@@ -582,22 +658,25 @@ int hb_search_layer(hb_index *ix, const void *host_queries, int64_t nq, const in
     }
     if (nq <= 0) return HB_OK;
     HB_CK(cudaSetDevice(ix->device));
-    cudaStream_t s = ix->stream;
+    ScanWs *wsp = ws_for_slot(ix, 0);
+    if (!wsp) { set_error("cannot create the scan workspace"); return HB_ECUDA; }
+    ScanWs &ws = *wsp;
+    cudaStream_t s = ws.own_stream;
     const int stride = std::max(ef, nep);
-    HB_CK(ix->ws_q.ensure((size_t) nq * ix->dim * ix->esize));
-    HB_CK(ix->ws_ep.ensure(sizeof(int32_t) * nq * nep));
-    HB_CK(ix->ws_elem.ensure(sizeof(int32_t) * nq * stride));
-    HB_CK(ix->ws_dist.ensure(sizeof(float) * nq * stride));
-    HB_CK(ix->ws_cnt.ensure(sizeof(int32_t) * nq));
-    HB_CK(cudaMemcpyAsync(ix->ws_q.p, host_queries, (size_t) nq * ix->dim * ix->esize, cudaMemcpyHostToDevice, s));
-    HB_CK(cudaMemcpyAsync(ix->ws_ep.p, ep, sizeof(int32_t) * nq * nep, cudaMemcpyHostToDevice, s));
-    int rc = scan_dev(ix, ix->ws_q.p, nq, ef, ix->ws_elem.as<int32_t>(), ix->ws_dist.as<float>(), ix->ws_cnt.as<int32_t>(), s,
-                      ix->ws_ep.as<int32_t>(), nep, layer);
+    HB_CK(ws.q.ensure((size_t) nq * ix->dim * ix->esize));
+    HB_CK(ws.ep.ensure(sizeof(int32_t) * nq * nep));
+    HB_CK(ws.elem.ensure(sizeof(int32_t) * nq * stride));
+    HB_CK(ws.dist.ensure(sizeof(float) * nq * stride));
+    HB_CK(ws.cnt.ensure(sizeof(int32_t) * nq));
+    HB_CK(cudaMemcpyAsync(ws.q.p, host_queries, (size_t) nq * ix->dim * ix->esize, cudaMemcpyHostToDevice, s));
+    HB_CK(cudaMemcpyAsync(ws.ep.p, ep, sizeof(int32_t) * nq * nep, cudaMemcpyHostToDevice, s));
+    int rc = scan_dev(ix, ws, ws.q.p, nq, ef, ws.elem.as<int32_t>(), ws.dist.as<float>(), ws.cnt.as<int32_t>(), s,
+                      ws.ep.as<int32_t>(), nep, layer);
     if (rc) return rc;
-    HB_CK(cudaMemcpyAsync(out_elem, ix->ws_elem.p, sizeof(int32_t) * nq * stride, cudaMemcpyDeviceToHost, s));
-    HB_CK(cudaMemcpyAsync(out_dist, ix->ws_dist.p, sizeof(float) * nq * stride, cudaMemcpyDeviceToHost, s));
-    if (out_cnt) HB_CK(cudaMemcpyAsync(out_cnt, ix->ws_cnt.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, s));
-    return check_status(ix, nq, s);
+    HB_CK(cudaMemcpyAsync(out_elem, ws.elem.p, sizeof(int32_t) * nq * stride, cudaMemcpyDeviceToHost, s));
+    HB_CK(cudaMemcpyAsync(out_dist, ws.dist.p, sizeof(float) * nq * stride, cudaMemcpyDeviceToHost, s));
+    if (out_cnt) HB_CK(cudaMemcpyAsync(out_cnt, ws.cnt.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, s));
+    return check_status(ix, ws, nq, s);
 }
 
 int hb_get_counters(hb_index *ix, hb_counters *out, int reset)
@@ -615,20 +694,20 @@ int hb_get_counters(hb_index *ix, hb_counters *out, int reset)
 
 int hb_get_per_query_counters(hb_index *ix, int64_t nq, int32_t *out)
 {
-    if (!ix || !out || !ix->ws_pq.p) { set_error("per-query counters are not enabled (hb_set_option per_query_counters 1)"); return HB_ESTATE; }
+    if (!ix || !out || !ix->last_ws || !ix->last_ws->pq.p) { set_error("per-query counters are not enabled (hb_set_option per_query_counters 1)"); return HB_ESTATE; }
     HB_CK(cudaSetDevice(ix->device));
     HB_CK(cudaDeviceSynchronize());
-    HB_CK(cudaMemcpy(out, ix->ws_pq.p, sizeof(int32_t) * 4 * nq, cudaMemcpyDeviceToHost));
+    HB_CK(cudaMemcpy(out, ix->last_ws->pq.p, sizeof(int32_t) * 4 * nq, cudaMemcpyDeviceToHost));
     return HB_OK;
 }
 
 float hb_last_search_ms(const hb_index *ix)
 {
-    if (!ix || !ix->timing_valid) return -1.f;
+    if (!ix || !ix->last_ws || !ix->last_ws->timing_valid) return -1.f;
     float ms = -1.f;
     cudaSetDevice(ix->device);
-    if (cudaEventSynchronize(ix->ev1) != cudaSuccess) return -1.f;
-    if (cudaEventElapsedTime(&ms, ix->ev0, ix->ev1) != cudaSuccess) return -1.f;
+    if (cudaEventSynchronize(ix->last_ws->ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, ix->last_ws->ev0, ix->last_ws->ev1) != cudaSuccess) return -1.f;
     return ms;
 }
 
@@ -694,13 +773,27 @@ int hb_distance_batch(hb_index *ix, const void *host_queries, int64_t nq, const 
     HB_CK(cudaMemcpyAsync(ix->ws_q.p, host_queries, (size_t) nq * ix->dim * ix->esize, cudaMemcpyHostToDevice, s));
     HB_CK(cudaMemcpyAsync(ix->ws_elem.p, cand, sizeof(int32_t) * nq * nc, cudaMemcpyHostToDevice, s));
     const void *q = nullptr;
-    int rc = prepare_queries(ix, ix->ws_q.p, nq, s, &q);
+    ScanWs *wsp = ws_for_slot(ix, 0);
+    if (!wsp) { set_error("cannot create the scan workspace"); return HB_ECUDA; }
+    int rc = prepare_queries(ix, *wsp, ix->ws_q.p, nq, s, &q);
     if (rc) return rc;
     DistBatchParams p;
     p.g = ix->view(); p.queries = q; p.nq = nq; p.cand = ix->ws_elem.as<int32_t>(); p.nc = nc; p.out = ix->ws_dist.as<float>();
     HB_CK(get_dist_launcher(ix->dtype, ix->metric != HB_L2)(p, s));
     HB_CK(cudaMemcpyAsync(out, ix->ws_dist.p, sizeof(float) * nq * nc, cudaMemcpyDeviceToHost, s));
     HB_CK(cudaStreamSynchronize(s));
+    return HB_OK;
+}
+
+int hb_distance_batch_dev(hb_index *ix, const void *dev_queries, int64_t nq, const int32_t *dev_cand, int nc, float *dev_out,
+                          void *stream)
+{
+    if (!ix || !dev_queries || !dev_cand || !dev_out || nc < 1) { set_error("hb_distance_batch_dev: bad argument"); return HB_EINVAL; }
+    if (nq <= 0) return HB_OK;
+    HB_CK(cudaSetDevice(ix->device));
+    DistBatchParams p;
+    p.g = ix->view(); p.queries = dev_queries; p.nq = nq; p.cand = dev_cand; p.nc = nc; p.out = dev_out;
+    HB_CK(get_dist_launcher(ix->dtype, ix->metric != HB_L2)(p, (cudaStream_t) stream));
     return HB_OK;
 }
 

@@ -247,7 +247,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         sp.efc = efc;
         sp.capW = ((efc + 16 + 3) / 4) * 4;
         {
-            int slots = 1; while (slots < efc * 32) slots <<= 1;
+            int slots = 1; while (slots < efc * 16) slots <<= 1;
             if (slots < 1024) slots = 1024;
             const size_t fixed = (size_t) ix->nvec * (ix->dtype == HB_F32 ? 4 : 8) * 4 + (size_t) sp.capW * 8 + 16;
             while (slots > 256 && (fixed + (size_t) slots * 4) * BUILD_WARPS > 200 * 1024) slots >>= 1;
@@ -273,6 +273,9 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         HB_CK(ix->ws_gwd.ensure(sizeof(float) * slow_warps * sp.gcap));
         HB_CK(ix->ws_gwi.ensure(sizeof(uint32_t) * slow_warps * sp.gcap));
         sp.gbits = ix->ws_gbits.as<uint32_t>(); sp.gwd = ix->ws_gwd.as<float>(); sp.gwi = ix->ws_gwi.as<uint32_t>();
+        sp.oslots = 4096;
+        HB_CK(ix->ws_ovf.ensure(sizeof(uint32_t) * (size_t) ix->num_sms * MAX_CTAS_PER_SM * BUILD_WARPS * sp.oslots));
+        sp.ovf = ix->ws_ovf.as<uint32_t>();
         HB_CK(HB_PICK(build_search, ix)(sp, ix->num_sms, slow_grid, s, false));
         BuildSearchParams sps = sp;
         sps.work = misc + 1; sps.qlist = sp.slow_list; sps.qcount = sp.slow_count;

@@ -13,7 +13,7 @@
 // A batch is what pgvector's parallel build workers are to each other: elements inserted
 // concurrently do not see one another.
 #pragma once
-#include "search_core.cuh"
+#include "scan_kernel.cuh"
 #include <cuda_runtime.h>
 
 namespace hb {
@@ -34,6 +34,7 @@ struct BuildSearchParams {
     const int32_t *qlist, *qcount;
     unsigned long long *totals;
     unsigned int *work;
+    uint32_t *ovf; int oslots;    // fast path: per-warp visited overflow table in HBM
     uint32_t *gbits; int gwords;
     float *gwd; uint32_t *gwi; int gcap;
 };
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_search_kernel(const Bu
     } else {
         unsigned char *s = base + (size_t) g.nvec * Vec<T>::VEC * 4;
         vs.tab = reinterpret_cast<uint32_t *>(s);
+        vs.set_overflow(p.ovf + ((size_t) blockIdx.x * BUILD_WARPS + warp) * p.oslots, p.oslots);
         w.d = reinterpret_cast<float *>(s + (size_t) p.slots * 4);
         w.id = reinterpret_cast<uint32_t *>(s + (size_t) p.slots * 4 + (size_t) p.capW * 4);
         w.cap = p.capW;
@@ -417,12 +419,13 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) nbr_dist_kernel(const NbrDis
 
 // ---- launch helpers ---------------------------------------------------------------------------
 #define HB_NV_DISPATCH(nvec, CALL)                                                                 \
-    switch (((nvec) + 31) / 32) {                                                                  \
+    switch (nv_of(nvec)) {                                                                         \
     case 1: CALL(1, 8); break;                                                                     \
     case 2: CALL(2, 8); break;                                                                     \
-    case 3: case 4: CALL(4, 4); break;                                                             \
-    case 5: case 6: CALL(6, 4); break;                                                             \
-    case 7: case 8: CALL(8, 2); break;                                                             \
+    case 3: CALL(3, 4); break;                                                                     \
+    case 4: CALL(4, 4); break;                                                                     \
+    case 6: CALL(6, 4); break;                                                                     \
+    case 8: CALL(8, 2); break;                                                                     \
     default: CALL(0, 2); break;                                                                    \
     }
 
@@ -439,6 +442,7 @@ cudaError_t launch_build_search_t(const BuildSearchParams &p, int num_sms, int s
             int bps = 0;                                                                           \
             err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, BUILD_WARPS * 32, smem); \
             if (err == cudaSuccess) {                                                              \
+                if (bps > MAX_CTAS_PER_SM) bps = MAX_CTAS_PER_SM;                                  \
                 if (bps < 1) err = cudaErrorInvalidConfiguration;                                  \
                 else {                                                                             \
                     int64_t want = SLOW ? slow_grid : (p.B + BUILD_WARPS - 1) / BUILD_WARPS;       \

@@ -40,29 +40,27 @@ template <> struct Vec<__half> { static constexpr int VEC = 8; };
 // lane's 128-bit read is bank-conflict free: q[4*ch + k] (k<4) and q[plane + 4*ch + (k-4)].
 template <typename T> __device__ __forceinline__ int query_floats(int nvec) { return nvec * Vec<T>::VEC; }
 
+// one 16-byte chunk of a row against the matching query components (already in registers)
 template <typename T, bool IP>
-__device__ __forceinline__ void accum_chunk(float (&acc)[Vec<T>::VEC], const uint4 &raw, const float *q,
-                                            int ch, int plane)
+__device__ __forceinline__ void accum_chunk(float (&acc)[Vec<T>::VEC], const uint4 &raw, const float4 &qa,
+                                            const float4 &qb)
 {
     if constexpr (sizeof(T) == 4) {
-        const float4 qv = *reinterpret_cast<const float4 *>(q + 4 * ch);
         const float v0 = __uint_as_float(raw.x), v1 = __uint_as_float(raw.y);
         const float v2 = __uint_as_float(raw.z), v3 = __uint_as_float(raw.w);
         if constexpr (IP) {
-            acc[0] = fmaf(qv.x, v0, acc[0]);
-            acc[1] = fmaf(qv.y, v1, acc[1]);
-            acc[2] = fmaf(qv.z, v2, acc[2]);
-            acc[3] = fmaf(qv.w, v3, acc[3]);
+            acc[0] = fmaf(qa.x, v0, acc[0]);
+            acc[1] = fmaf(qa.y, v1, acc[1]);
+            acc[2] = fmaf(qa.z, v2, acc[2]);
+            acc[3] = fmaf(qa.w, v3, acc[3]);
         } else {
             float t;
-            t = qv.x - v0; acc[0] = fmaf(t, t, acc[0]);
-            t = qv.y - v1; acc[1] = fmaf(t, t, acc[1]);
-            t = qv.z - v2; acc[2] = fmaf(t, t, acc[2]);
-            t = qv.w - v3; acc[3] = fmaf(t, t, acc[3]);
+            t = qa.x - v0; acc[0] = fmaf(t, t, acc[0]);
+            t = qa.y - v1; acc[1] = fmaf(t, t, acc[1]);
+            t = qa.z - v2; acc[2] = fmaf(t, t, acc[2]);
+            t = qa.w - v3; acc[3] = fmaf(t, t, acc[3]);
         }
     } else {
-        const float4 qa = *reinterpret_cast<const float4 *>(q + 4 * ch);
-        const float4 qb = *reinterpret_cast<const float4 *>(q + plane + 4 * ch);
         const float2 h0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
         const float2 h1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
         const float2 h2 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.z));
@@ -97,48 +95,51 @@ template <int VEC> __device__ __forceinline__ float fold_lane(const float (&a)[V
 }
 
 // Lane partials of G candidate rows against the query in shared memory.
-// NV > 0: chunks per lane known at compile time (FULLROW: nvec == 32*NV, no bounds checks);
-// NV == 0: run-time loop (any dimension).
-template <typename T, bool IP, int NV, bool FULLROW, int G>
-__device__ __forceinline__ void group_partials(const char *__restrict__ vecs, size_t row_bytes, int nvec,
+// NV > 0: the row is exactly 32*NV chunks (every lane owns NV chunks; loads are issued
+// back-to-back from one base pointer per row with immediate offsets, G*NV 128-bit loads in flight
+// per lane); NV == 0: run-time loop for any row length.
+template <typename T, bool IP, int NV, int G>
+__device__ __forceinline__ void group_partials(const char *__restrict__ vecs, uint32_t row_bytes, int nvec,
                                                const float *q, const int32_t (&ids)[G], int lane,
                                                float (&part)[G])
 {
     constexpr int VEC = Vec<T>::VEC;
-    const int plane = 4 * nvec;
+    constexpr bool HALF = sizeof(T) == 2;
     float acc[G][VEC];
 #pragma unroll
     for (int c = 0; c < G; c++)
 #pragma unroll
         for (int k = 0; k < VEC; k++) acc[c][k] = 0.0f;
+    const char *rp[G];
+#pragma unroll
+    for (int c = 0; c < G; c++) rp[c] = vecs + (uint64_t) (uint32_t) ids[c] * row_bytes + 16 * lane;
+    const float *qp = q + 4 * lane;
 
     if constexpr (NV > 0) {
         uint4 raw[G][NV];
 #pragma unroll
-        for (int c = 0; c < G; c++) {
-            const char *row = vecs + (size_t) ids[c] * row_bytes;
+        for (int c = 0; c < G; c++)
 #pragma unroll
-            for (int j = 0; j < NV; j++) {
-                const int ch = lane + 32 * j;
-                if (FULLROW || ch < nvec) raw[c][j] = ldg_stream(row + 16 * ch);
-                else raw[c][j] = make_uint4(0, 0, 0, 0);
-            }
-        }
+            for (int j = 0; j < NV; j++) raw[c][j] = ldg_stream(rp[c] + 512 * j);
 #pragma unroll
         for (int j = 0; j < NV; j++) {
-            const int ch = lane + 32 * j;
-            if (FULLROW || ch < nvec) {
+            const float4 qa = *reinterpret_cast<const float4 *>(qp + 128 * j);
+            float4 qb = qa;
+            if constexpr (HALF) qb = *reinterpret_cast<const float4 *>(qp + 128 * (NV + j));
 #pragma unroll
-                for (int c = 0; c < G; c++) accum_chunk<T, IP>(acc[c], raw[c][j], q, ch, plane);
-            }
+            for (int c = 0; c < G; c++) accum_chunk<T, IP>(acc[c], raw[c][j], qa, qb);
         }
     } else {
+        const int plane = 4 * nvec;
         for (int ch = lane; ch < nvec; ch += 32) {
             uint4 raw[G];
 #pragma unroll
-            for (int c = 0; c < G; c++) raw[c] = ldg_stream(vecs + (size_t) ids[c] * row_bytes + 16 * ch);
+            for (int c = 0; c < G; c++) raw[c] = ldg_stream(rp[c] + 16 * (ch - lane));
+            const float4 qa = *reinterpret_cast<const float4 *>(q + 4 * ch);
+            float4 qb = qa;
+            if constexpr (HALF) qb = *reinterpret_cast<const float4 *>(q + plane + 4 * ch);
 #pragma unroll
-            for (int c = 0; c < G; c++) accum_chunk<T, IP>(acc[c], raw[c], q, ch, plane);
+            for (int c = 0; c < G; c++) accum_chunk<T, IP>(acc[c], raw[c], qa, qb);
         }
     }
 #pragma unroll
@@ -173,12 +174,12 @@ template <> struct XReduce<1> {
 };
 
 // distances of G candidates; result of candidate c is returned in every lane via out[c]
-template <typename T, bool IP, int NV, bool FULLROW, int G>
-__device__ __forceinline__ float group_distance(const char *__restrict__ vecs, size_t row_bytes, int nvec,
+template <typename T, bool IP, int NV, int G>
+__device__ __forceinline__ float group_distance(const char *__restrict__ vecs, uint32_t row_bytes, int nvec,
                                                 const float *q, const int32_t (&ids)[G], int lane)
 {
     float part[G];
-    group_partials<T, IP, NV, FULLROW, G>(vecs, row_bytes, nvec, q, ids, lane, part);
+    group_partials<T, IP, NV, G>(vecs, row_bytes, nvec, q, ids, lane, part);
     const float s = XReduce<G>::run(part, lane, 16);
     return IP ? -s : s;   // lane (c * 32/G) .. hold candidate c
 }

@@ -3,6 +3,7 @@
 #include "../../include/hnsw_b200.h"
 #include "search_core.cuh"
 #include <cuda_runtime.h>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -36,6 +37,28 @@ struct DevBuf {
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// everything one in-flight scan batch needs; one per user stream (device API) or per async slot
+struct ScanWs {
+    cudaStream_t own_stream = nullptr;      // slots of the host API own a stream
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf q, qn, elem, dist, cnt, status, slow, misc, pq, tids, tdist, gbits, gwd, gwi, ep, ovf;
+    bool timing_valid = false;
+    // pending asynchronous host-API call
+    int64_t pending_nq = 0;
+    bool pending = false;
+    int32_t *h_err = nullptr;               // pinned: error flag of the last batch
+    void release()
+    {
+        if (h_err) cudaFreeHost(h_err);
+        DevBuf *b[] = { &q, &qn, &elem, &dist, &cnt, &status, &slow, &misc, &pq, &tids, &tdist, &gbits, &gwd, &gwi, &ep, &ovf };
+        for (auto x : b) x->release();
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
+};
+constexpr int ASYNC_SLOTS = 4;
+
 }   // namespace hb
 
 struct hb_index {
@@ -65,13 +88,16 @@ struct hb_index {
     std::vector<int64_t> h_tids;   // n x HB_HEAPTIDS
 
     // tuning knobs (0 = automatic)
-    int opt_slots = 0, opt_grid = 0, opt_build_batch = 0, opt_per_query = 0;
+    int opt_slots = 0, opt_grid = 0, opt_build_batch = 0, opt_per_query = 0, opt_variant = 0, opt_no_slow = 0;
 
     // workspaces
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    hb::DevBuf ws_q, ws_qn, ws_elem, ws_dist, ws_cnt, ws_status, ws_slow, ws_misc, ws_pq, ws_tids, ws_tdist;
-    hb::DevBuf ws_gbits, ws_gwd, ws_gwi, ws_ep;
+    hb::DevBuf ws_q, ws_qn, ws_elem, ws_dist, ws_status, ws_misc;   // opclass support functions, build
+    hb::DevBuf ws_gbits, ws_gwd, ws_gwi, ws_ovf;                    // build-search scratch
+    hb::ScanWs *slot_ws[hb::ASYNC_SLOTS] = { nullptr, nullptr, nullptr, nullptr };
+    std::map<void *, hb::ScanWs *> stream_ws;                       // device API: one workspace per user stream
+    hb::ScanWs *last_ws = nullptr;
     hb::DevBuf ws_build[12];
     unsigned long long *d_totals = nullptr;   // n_dist, n_hop0, n_hopu, n_slow, n_pair, ...
     hb_counters host_totals = {0, 0, 0, 0, 0};

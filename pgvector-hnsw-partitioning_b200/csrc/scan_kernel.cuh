@@ -12,6 +12,7 @@
 namespace hb {
 
 constexpr int SCAN_WARPS = 4;   // warps (= concurrent queries) per CTA
+constexpr int MAX_CTAS_PER_SM = 8;   // cap on resident CTAs per SM (sizes the per-warp overflow tables)
 
 struct ScanParams {
     GraphView g;
@@ -27,14 +28,17 @@ struct ScanParams {
     int32_t *status;           // nq
     int32_t *slow_list;        // fast path appends queries whose visited table / tie tail overflowed
     int32_t *slow_count;
+    int32_t *err;              // set to 1 when a query could not be completed (tie tail beyond HB_TIE_LIMIT)
     int32_t *per_query;        // optional nq x 4: n_dist, n_hop0, n_hopu, path
     unsigned long long *totals;   // n_dist, n_hop0, n_hopu, n_slow
     unsigned int *work;
     // slow-path scratch in HBM, one slice per resident warp
+    uint32_t *ovf; int oslots;    // fast path: per-warp visited overflow table in HBM
     uint32_t *gbits; int gwords;
     float *gwd; uint32_t *gwi; int gcap;
     // single-layer mode (unit tests): explicit entry points
     const int32_t *ep; int nep; int layer;
+    int variant;               // host only: tuning variant of the unrolled kernel (0 = default)
 };
 
 template <typename T> __host__ __device__ inline size_t scan_warp_smem(int nvec, int capW, int slots, bool slow)
@@ -44,8 +48,8 @@ template <typename T> __host__ __device__ inline size_t scan_warp_smem(int nvec,
     return (b + 15) & ~(size_t) 15;
 }
 
-template <typename T, bool IP, int NV, int G, bool SLOW>
-__global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams p)
+template <typename T, bool IP, int NV, int G, bool SLOW, int MINB>
+__global__ void __launch_bounds__(SCAN_WARPS * 32, MINB) scan_kernel(const ScanParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -67,6 +71,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
     } else {
         unsigned char *s = base + (size_t) g.nvec * Vec<T>::VEC * 4;
         vs.tab = reinterpret_cast<uint32_t *>(s);
+        vs.set_overflow(p.ovf + ((size_t) blockIdx.x * SCAN_WARPS + warp) * p.oslots, p.oslots);
         w.d = reinterpret_cast<float *>(s + (size_t) p.slots * 4);
         w.id = reinterpret_cast<uint32_t *>(s + (size_t) p.slots * 4 + (size_t) p.capW * 4);
         w.cap = p.capW;
@@ -139,6 +144,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
         if (lane == 0) {
             p.out_cnt[qi] = cnt;
             p.status[qi] = st == ST_OK ? 0 : -st;
+            if (st != ST_OK) atomicExch(p.err, 1);
             atomicAdd(p.totals + 0, (unsigned long long) ctr.n_dist);
             atomicAdd(p.totals + 1, (unsigned long long) ctr.n_hop0);
             atomicAdd(p.totals + 2, (unsigned long long) ctr.n_hopu);
@@ -156,11 +162,11 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_kernel(const ScanParams 
 // host-side launch helper -------------------------------------------------------------------
 struct ScanLaunchInfo { int grid; size_t smem; int blocks_per_sm; };
 
-template <typename T, bool IP, int NV, int G, bool SLOW>
+template <typename T, bool IP, int NV, int G, bool SLOW, int MINB>
 cudaError_t launch_scan_variant(const ScanParams &p, int num_sms, int max_grid, cudaStream_t stream,
                                 ScanLaunchInfo *info)
 {
-    auto kern = scan_kernel<T, IP, NV, G, SLOW>;
+    auto kern = scan_kernel<T, IP, NV, G, SLOW, MINB>;
     const size_t smem = scan_warp_smem<T>(p.g.nvec, p.capW, p.slots, SLOW) * SCAN_WARPS;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
@@ -168,6 +174,7 @@ cudaError_t launch_scan_variant(const ScanParams &p, int num_sms, int max_grid, 
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SCAN_WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     if (bps < 1) return cudaErrorInvalidConfiguration;
+    if (bps > MAX_CTAS_PER_SM) bps = MAX_CTAS_PER_SM;
     int64_t want = SLOW ? max_grid : (p.nq + SCAN_WARPS - 1) / SCAN_WARPS;
     int grid = (int) (want < (int64_t) bps * num_sms ? want : (int64_t) bps * num_sms);
     if (max_grid > 0 && grid > max_grid) grid = max_grid;
@@ -177,24 +184,37 @@ cudaError_t launch_scan_variant(const ScanParams &p, int num_sms, int max_grid, 
     return cudaGetLastError();
 }
 
-// pick the chunks-per-lane specialisation for the row length
+// pick the chunks-per-lane specialisation: rows of exactly 32*NV 16-byte chunks get the unrolled
+// kernels (NV, rows in flight G, min CTAs per SM); any other row length runs the generic loop.
+#define HB_NV_TABLE(X) X(1, 8, 5) X(2, 8, 4) X(3, 4, 4) X(4, 4, 4) X(6, 4, 4) X(8, 2, 4)
+inline int nv_of(int nvec)
+{
+    if (nvec % 32) return 0;
+    const int nv = nvec / 32;
+    return (nv == 1 || nv == 2 || nv == 3 || nv == 4 || nv == 6 || nv == 8) ? nv : 0;
+}
+
 template <typename T, bool IP, bool SLOW>
 cudaError_t launch_scan_t(const ScanParams &p, int num_sms, int max_grid, cudaStream_t stream,
                           ScanLaunchInfo *info)
 {
-    const int nv = (p.g.nvec + 31) / 32;
-    if constexpr (SLOW) return launch_scan_variant<T, IP, 0, 2, true>(p, num_sms, max_grid, stream, info);
+    if constexpr (SLOW) return launch_scan_variant<T, IP, 0, 2, true, 1>(p, num_sms, max_grid, stream, info);
     else {
-        switch (nv) {
-        case 1: return launch_scan_variant<T, IP, 1, 8, false>(p, num_sms, max_grid, stream, info);
-        case 2: return launch_scan_variant<T, IP, 2, 8, false>(p, num_sms, max_grid, stream, info);
-        case 3:
-        case 4: return launch_scan_variant<T, IP, 4, 4, false>(p, num_sms, max_grid, stream, info);
-        case 5:
-        case 6: return launch_scan_variant<T, IP, 6, 4, false>(p, num_sms, max_grid, stream, info);
-        case 7:
-        case 8: return launch_scan_variant<T, IP, 8, 2, false>(p, num_sms, max_grid, stream, info);
-        default: return launch_scan_variant<T, IP, 0, 2, false>(p, num_sms, max_grid, stream, info);
+        if (nv_of(p.g.nvec) == 6 && p.variant) {
+            switch (p.variant) {
+            case 1: return launch_scan_variant<T, IP, 6, 4, false, 3>(p, num_sms, max_grid, stream, info);
+            case 2: return launch_scan_variant<T, IP, 6, 2, false, 4>(p, num_sms, max_grid, stream, info);
+            case 3: return launch_scan_variant<T, IP, 6, 2, false, 5>(p, num_sms, max_grid, stream, info);
+            case 4: return launch_scan_variant<T, IP, 6, 2, false, 6>(p, num_sms, max_grid, stream, info);
+            case 5: return launch_scan_variant<T, IP, 6, 1, false, 6>(p, num_sms, max_grid, stream, info);
+            default: break;
+            }
+        }
+        switch (nv_of(p.g.nvec)) {
+#define HB_CASE(NVV, GG, MB) case NVV: return launch_scan_variant<T, IP, NVV, GG, false, MB>(p, num_sms, max_grid, stream, info);
+            HB_NV_TABLE(HB_CASE)
+#undef HB_CASE
+        default: return launch_scan_variant<T, IP, 0, 2, false, 4>(p, num_sms, max_grid, stream, info);
         }
     }
 }
@@ -209,7 +229,7 @@ struct DistBatchParams {
     float *out;            // nq x nc
 };
 
-template <typename T, bool IP>
+template <typename T, bool IP, int NV, int G>
 __global__ void __launch_bounds__(SCAN_WARPS * 32) dist_batch_kernel(const DistBatchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -226,7 +246,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) dist_batch_kernel(const DistB
         __syncwarp();
         const int32_t nb = c < p.nc ? p.cand[qi * p.nc + c] : -1;
         const unsigned mask = __ballot_sync(FULL, nb >= 0 && nb < g.n);
-        const float d = eval_candidates<T, IP, 0, 2>(g, q, nb, mask, lane);
+        const float d = eval_candidates<T, IP, NV, G>(g, q, nb, mask, lane);
         if (c < p.nc) p.out[qi * p.nc + c] = d;
     }
 }
@@ -235,15 +255,31 @@ template <typename T, bool IP>
 cudaError_t launch_dist_t(const DistBatchParams &p, cudaStream_t stream)
 {
     const size_t smem = scan_warp_smem<T>(p.g.nvec, 0, 0, true) * SCAN_WARPS;
-    auto kern = dist_batch_kernel<T, IP>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (e != cudaSuccess) return e;
     const int64_t items = p.nq * ((p.nc + 31) / 32);
     int64_t grid = (items + SCAN_WARPS - 1) / SCAN_WARPS;
     if (grid > 148 * 16) grid = 148 * 16;
     if (grid < 1) grid = 1;
-    kern<<<(int) grid, SCAN_WARPS * 32, smem, stream>>>(p);
-    return cudaGetLastError();
+    cudaError_t e = cudaSuccess;
+#define HB_DCASE(NVV, GG)                                                                          \
+    {                                                                                              \
+        auto kern = dist_batch_kernel<T, IP, NVV, GG>;                                             \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);   \
+        if (e == cudaSuccess) {                                                                    \
+            kern<<<(int) grid, SCAN_WARPS * 32, smem, stream>>>(p);                                \
+            e = cudaGetLastError();                                                                \
+        }                                                                                          \
+    }
+    switch (nv_of(p.g.nvec)) {
+    case 1: HB_DCASE(1, 8) break;
+    case 2: HB_DCASE(2, 8) break;
+    case 3: HB_DCASE(3, 4) break;
+    case 4: HB_DCASE(4, 4) break;
+    case 6: HB_DCASE(6, 4) break;
+    case 8: HB_DCASE(8, 2) break;
+    default: HB_DCASE(0, 2) break;
+    }
+#undef HB_DCASE
+    return e;
 }
 
 }   // namespace hb

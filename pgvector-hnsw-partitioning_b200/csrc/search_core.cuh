@@ -46,32 +46,87 @@ struct WList {               // sorted (distance, id) array; warp-uniform bookke
 };
 
 // ---- visited sets ---------------------------------------------------------------------------
-struct VisitedHash {         // shared memory, open addressing, linear probing
-    uint32_t *tab;
+struct VisitedHash {         // shared-memory table + per-warp overflow table in HBM (both exact)
+    uint32_t *tab;           // shared memory, open addressing, linear probing
     int slots, shift, count, limit;
+    uint32_t *otab;          // overflow: used only once the shared table reached its load limit
+    int oslots, oshift, ocount, olimit;
+    bool odirty;
     __device__ __forceinline__ void configure(int s)
     {
         slots = s;
         shift = 32 - (31 - __clz(s));
         limit = s - (s >> 2);             // 75 % load
     }
+    __device__ __forceinline__ void set_overflow(uint32_t *t, int s)
+    {
+        otab = t; oslots = s; odirty = true;   // first clear() wipes it
+        oshift = s > 1 ? 32 - (31 - __clz(s)) : 32;
+        olimit = s - (s >> 2);
+        ocount = 0;
+    }
     __device__ __forceinline__ void clear(int lane)
     {
         uint4 *t = reinterpret_cast<uint4 *>(tab);
         for (int i = lane; i < slots / 4; i += 32) t[i] = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
         count = 0;
+        if (odirty) {
+            uint4 *o = reinterpret_cast<uint4 *>(otab);
+            for (int i = lane; i < oslots / 4; i += 32) o[i] = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
+            odirty = false;
+            ocount = 0;
+        }
         __syncwarp();
     }
-    __device__ __forceinline__ bool room(int incoming) const { return count + incoming <= limit; }
-    __device__ __forceinline__ bool insert(uint32_t key)   // may be called by a subset of lanes
+    // room for `incoming` more keys?  (warp-uniform)
+    __device__ __forceinline__ bool room(int incoming) const
+    {
+        return count + incoming <= limit || ocount + incoming <= olimit;
+    }
+    // warp-uniform: where does this batch of `incoming` keys go
+    // (sticky: once a batch spilled, every later batch of this layer search goes to the overflow
+    // table, so a key lives in exactly one of the two tables)
+    __device__ __forceinline__ bool spill(int incoming) const { return ocount > 0 || count + incoming > limit; }
+
+    __device__ __forceinline__ static bool probe_insert(uint32_t *t, uint32_t mask, uint32_t h, uint32_t key)
+    {
+        // most probes find the key already present (neighbour lists overlap heavily): a plain
+        // load answers those; only an empty slot needs the CAS.  Slots only ever go EMPTY -> key.
+        for (;;) {
+            const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(t + h);
+            if (cur == key) return false;
+            if (cur == EMPTY) {
+                const uint32_t old = atomicCAS(t + h, EMPTY, key);
+                if (old == EMPTY) return true;
+                if (old == key) return false;
+            }
+            h = (h + 1) & mask;
+        }
+    }
+    __device__ __forceinline__ bool contains(uint32_t key) const
     {
         uint32_t h = (key * 0x9E3779B1u) >> shift;
         for (;;) {
-            const uint32_t old = atomicCAS(tab + h, EMPTY, key);
-            if (old == EMPTY) return true;
-            if (old == key) return false;
+            const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(tab + h);
+            if (cur == key) return true;
+            if (cur == EMPTY) return false;
             h = (h + 1) & (slots - 1);
         }
+    }
+    // insert one key; `to_overflow` is the warp-uniform decision of spill() for this batch.
+    // Returns true when the key was new.  May be called by a subset of lanes.
+    __device__ __forceinline__ bool insert(uint32_t key, bool to_overflow)
+    {
+        const uint32_t hk = key * 0x9E3779B1u;
+        if (!to_overflow) return probe_insert(tab, slots - 1, hk >> shift, key);
+        if (contains(key)) return false;
+        return probe_insert(otab, oslots - 1, oshift >= 32 ? 0u : hk >> oshift, key);
+    }
+    // account for `n_new` keys inserted by the last batch
+    __device__ __forceinline__ void added(int n_new, bool to_overflow)
+    {
+        if (to_overflow) { ocount += n_new; odirty = true; }
+        else count += n_new;
     }
 };
 
@@ -86,11 +141,13 @@ struct VisitedBitmap {       // HBM, one bit per element (large-visited-set path
         __syncwarp();
     }
     __device__ __forceinline__ bool room(int) const { return true; }
-    __device__ __forceinline__ bool insert(uint32_t key)
+    __device__ __forceinline__ bool spill(int) const { return false; }
+    __device__ __forceinline__ bool insert(uint32_t key, bool)
     {
         const uint32_t bit = 1u << (key & 31);
         return (atomicOr(bits + (key >> 5), bit) & bit) == 0;
     }
+    __device__ __forceinline__ void added(int n_new, bool) { count += n_new; }
 };
 
 // ---- W list ---------------------------------------------------------------------------------
@@ -147,15 +204,16 @@ __device__ __forceinline__ void wlist_as_entries(WList &w, VS &vs, int keep, int
 {
     if (w.L > keep) w.L = keep;
     vs.clear(lane);
+    const bool sp = vs.spill(w.L);
     for (int base = 0; base < w.L; base += 32) {
         const int i = base + lane;
         if (i < w.L) {
             const uint32_t id = w.id[i] & ID_MASK;
             w.id[i] = id;
-            vs.insert(id);
+            vs.insert(id, sp);
         }
     }
-    vs.count = w.L;
+    vs.added(w.L, sp);
     __syncwarp();
 }
 
@@ -179,7 +237,7 @@ __device__ __forceinline__ float eval_candidates(const GraphView &g, const float
             rem &= rem - 1;                                                                        \
             ids[c] = __shfl_sync(FULL, nb, src[c]);                                                \
         }                                                                                          \
-        const float s = group_distance<T, IP, NV, false, GG>(g.vecs, g.row_bytes, g.nvec, q, ids, lane); \
+        const float s = group_distance<T, IP, NV, GG>(g.vecs, (uint32_t) g.row_bytes, g.nvec, q, ids, lane); \
         _Pragma("unroll") for (int c = 0; c < GG; c++)                                             \
         {                                                                                          \
             const float v = __shfl_sync(FULL, s, c * (32 / GG));                                   \
@@ -223,11 +281,12 @@ __device__ __forceinline__ int search_layer(const GraphView &g, WList &w, VS &vs
         for (int cb = 0; cb < deg; cb += 32) {
             const int i = cb + lane;
             const int32_t nb = i < deg ? list[i] : -1;
+            const bool sp = vs.spill(min(32, deg - cb));
             bool isnew = false;
-            if (nb >= 0) isnew = vs.insert((uint32_t) nb);
+            if (nb >= 0) isnew = vs.insert((uint32_t) nb, sp);
             const unsigned nmask = __ballot_sync(FULL, isnew);
             if (nmask == 0) continue;
-            vs.count += __popc(nmask);
+            vs.added(__popc(nmask), sp);
             ctr.n_dist += __popc(nmask);
             const float myd = eval_candidates<T, IP, NV, G>(g, q, nb, nmask, lane);
             const bool full = w.L >= ef;
@@ -252,7 +311,7 @@ template <typename T, bool IP, int NV>
 __device__ __forceinline__ float one_distance(const GraphView &g, const float *q, int32_t e, int lane)
 {
     const int32_t ids[1] = { e };
-    return group_distance<T, IP, NV, false, 1>(g.vecs, g.row_bytes, g.nvec, q, ids, lane);
+    return group_distance<T, IP, NV, 1>(g.vecs, (uint32_t) g.row_bytes, g.nvec, q, ids, lane);
 }
 
 }   // namespace hb

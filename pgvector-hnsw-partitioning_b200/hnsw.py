@@ -78,6 +78,8 @@ _SIGS = {
     "hb_gettuple": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_endscan": (None, [C.c_void_p]),
     "hb_search_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_search_batch_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_search_batch_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "hb_search_batch_elements": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_search_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_search_layer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -85,6 +87,7 @@ _SIGS = {
     "hb_get_per_query_counters": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "hb_last_search_ms": (C.c_float, [C.c_void_p]),
     "hb_distance_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
+    "hb_distance_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "hb_normalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "hb_bruteforce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "hb_partition_of": (C.c_int, [C.c_int64, C.c_int]),
@@ -261,6 +264,14 @@ class HnswIndex:
         self._ck(self._L.hb_search_batch(self._h, C.c_void_p(q_ptr), nq, ef_search, k, C.c_void_p(tids_ptr),
                                          C.c_void_p(dist_ptr), C.c_void_p(cnt_ptr)), "hb_search_batch")
 
+    def search_async(self, slot, q_ptr, nq, k, ef_search, tids_ptr, dist_ptr, cnt_ptr):
+        """hb_search_batch_async on raw (pinned) host pointers; complete with search_wait(slot)."""
+        self._ck(self._L.hb_search_batch_async(self._h, slot, C.c_void_p(q_ptr), nq, ef_search, k, C.c_void_p(tids_ptr),
+                                               C.c_void_p(dist_ptr), C.c_void_p(cnt_ptr)), "hb_search_batch_async")
+
+    def search_wait(self, slot):
+        self._ck(self._L.hb_search_batch_wait(self._h, slot), "hb_search_batch_wait")
+
     def search_elements(self, queries, ef_search=40):
         q = self._vecs(queries)
         nq = q.shape[0]
@@ -316,6 +327,10 @@ class HnswIndex:
         out = np.empty(cand.shape, np.float32)
         self._ck(self._L.hb_distance_batch(self._h, _p(q), q.shape[0], _p(cand), cand.shape[1], _p(out)), "hb_distance_batch")
         return out
+
+    def distance_dev(self, dev_queries, nq, dev_cand, nc, dev_out, stream=0):
+        self._ck(self._L.hb_distance_batch_dev(self._h, C.c_void_p(dev_queries), nq, C.c_void_p(dev_cand), nc,
+                                               C.c_void_p(dev_out), C.c_void_p(stream)), "hb_distance_batch_dev")
 
     def normalize(self, vecs):
         """l2_normalize (FUNCTION 2 + normalisation) -> (normalised, ok mask)."""

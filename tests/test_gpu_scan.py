@@ -183,14 +183,15 @@ def test_scan_edge_cases(oracle, pkg):
     ix.close()
 
 
-def test_large_visited_set_path(oracle, pkg):
-    """a visited table too small for the query hands it to the bitmap path; results unchanged."""
+@pytest.mark.parametrize("slots", [64, 256])
+def test_visited_overflow_table(oracle, pkg, slots):
+    """a shared-memory visited table too small for the query spills into the per-warp overflow table
+    in HBM (and, past that, to the bitmap path); results unchanged."""
     x = sift_like(5000, 32, seed=3)
     q = sift_like(200, 32, seed=4)
     orc, ix = make(oracle, pkg, x, oracle.L2)
-    ix.set_option("slots", 256)
-    c = check_scan(oracle, orc, ix, q, 100, natural_check=False)
-    assert c["n_slow"] > 0
+    ix.set_option("slots", slots)
+    check_scan(oracle, orc, ix, q, 100, natural_check=False)
     ix.close()
 
 
@@ -198,10 +199,23 @@ def test_many_exact_ties(oracle, pkg):
     """very low-entropy data: long runs of equal distances at the ef boundary (tail overflow ->
     large-list path)."""
     rng = np.random.default_rng(5)
-    x = rng.integers(0, 2, (3000, 12)).astype(np.float32)
-    q = rng.integers(0, 2, (100, 12)).astype(np.float32)
+    x = rng.integers(0, 2, (3000, 8)).astype(np.float32)
+    q = rng.integers(0, 2, (100, 8)).astype(np.float32)
     orc, ix = make(oracle, pkg, x, oracle.L2, m=8, efc=32)
     c = check_scan(oracle, orc, ix, q, 20, natural_check=False)
+    ix.close()
+
+
+def test_tie_tail_overflow_uses_long_list_path(oracle, pkg):
+    """many duplicates of few distinct vectors: the run of equal distances at the ef boundary is longer
+    than the shared-memory tail, so those queries re-run on the long-list / bitmap path."""
+    rng = np.random.default_rng(6)
+    base = rng.integers(0, 3, (4, 6)).astype(np.float32)
+    x = base[rng.integers(0, 4, 2500)]
+    q = base[rng.integers(0, 4, 60)]
+    orc, ix = make(oracle, pkg, x, oracle.L2, m=8, efc=32)
+    c = check_scan(oracle, orc, ix, q, 10, natural_check=False)
+    assert c["n_slow"] > 0
     ix.close()
 
 
