@@ -17,6 +17,27 @@ def owned_partitions(n_partitions, rank, world):
     return [p for p in range(n_partitions) if p % world == rank]
 
 
+def exchange_topk(local_tids, local_dist, world, group=None):
+    """The one data-path collective: all-gather of every rank's nq x k (tid, distance) list into
+    world x nq x k.  Works on CUDA tensors (NCCL) and, for the host-logic tests, CPU tensors (gloo)."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return local_tids[None], local_dist[None]
+    nq, k = local_tids.shape
+    all_t = torch.empty((world, nq, k), dtype=local_tids.dtype, device=local_tids.device)
+    all_d = torch.empty((world, nq, k), dtype=local_dist.dtype, device=local_dist.device)
+    dist.all_gather_into_tensor(all_t.view(world * nq, k), local_tids.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_d.view(world * nq, k), local_dist.contiguous(), group=group)
+    return all_t, all_d
+
+
+def split_rows(heap_tids, n_partitions, rank, world):
+    """Rows this rank indexes: {partition -> row indices}, for the partitions it owns."""
+    part = partition_route(heap_tids, n_partitions)
+    return {p: np.nonzero(part == p)[0] for p in owned_partitions(n_partitions, rank, world)}
+
+
 class PartitionedIndex:
     def __init__(self, dim, opclass="vector_l2_ops", n_partitions=8, m=16, ef_construction=64,
                  capacity_per_partition=1 << 20, rank=0, world=1, device=0, seed=0, group=None):
@@ -38,10 +59,10 @@ class PartitionedIndex:
     def build(self, vecs, heap_tids=None):
         n = vecs.shape[0]
         tids = np.arange(n, dtype=np.int64) if heap_tids is None else np.ascontiguousarray(heap_tids, np.int64)
-        part = partition_route(tids, self.P)
+        rows = split_rows(tids, self.P, self.rank, self.world)
         total = 0
         for p, ix in self.parts.items():
-            sel = np.nonzero(part == p)[0]
+            sel = rows[p]
             if len(sel):
                 total += ix.insert(vecs[sel], tids[sel])
         return total
@@ -78,17 +99,7 @@ class PartitionedIndex:
         return out_t, out_d
 
     def exchange(self, local_tids, local_dist):
-        """The one collective: all-gather of every rank's nq x k list -> world x nq x k."""
-        import torch
-        import torch.distributed as dist
-        if self.world == 1:
-            return local_tids[None], local_dist[None]
-        nq, k = local_tids.shape
-        all_t = torch.empty((self.world, nq, k), dtype=local_tids.dtype, device=local_tids.device)
-        all_d = torch.empty((self.world, nq, k), dtype=local_dist.dtype, device=local_dist.device)
-        dist.all_gather_into_tensor(all_t, local_tids.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(all_d, local_dist.contiguous(), group=self.group)
-        return all_t, all_d
+        return exchange_topk(local_tids, local_dist, self.world, self.group)
 
     def search_dev(self, q_dev, k=10, ef_search=40):
         """Broadcast queries are assumed resident on every rank.  Returns merged nq x k CUDA tensors

@@ -207,12 +207,12 @@ def test_many_exact_ties(oracle, pkg):
 
 
 def test_tie_tail_overflow_uses_long_list_path(oracle, pkg):
-    """many duplicates of few distinct vectors: the run of equal distances at the ef boundary is longer
-    than the shared-memory tail, so those queries re-run on the long-list / bitmap path."""
+    """all points of the {0,1}^10 lattice: 45 (120, 210 ...) distinct elements tie exactly at the ef
+    boundary, more than the shared-memory tie tail holds, so those queries re-run on the long-list /
+    bitmap path."""
     rng = np.random.default_rng(6)
-    base = rng.integers(0, 3, (4, 6)).astype(np.float32)
-    x = base[rng.integers(0, 4, 2500)]
-    q = base[rng.integers(0, 4, 60)]
+    x = np.array([[(i >> b) & 1 for b in range(10)] for i in range(1024)], np.float32)[rng.permutation(1024)]
+    q = x[rng.integers(0, 1024, 60)]
     orc, ix = make(oracle, pkg, x, oracle.L2, m=8, efc=32)
     c = check_scan(oracle, orc, ix, q, 10, natural_check=False)
     assert c["n_slow"] > 0
