@@ -157,6 +157,11 @@ int hb_normalize(hb_index *ix, const void *host_in, int64_t n, void *host_out, u
 /* ---- exact scan of a partition (recall ground truth; bf16 tcgen05 GEMM + fp32 re-rank) ------ */
 int hb_bruteforce(hb_index *ix, const void *host_queries, int64_t nq, int k, int32_t *out_elem,
                   float *out_dist);
+/* same, with diagnostics: dbg_scores (optional, host, nq x n) receives the raw bf16 GEMM scores;
+ * stats (optional, 3 floats): queries certified exact by the bf16 error bound, queries re-scanned
+ * exhaustively in fp32, GEMM kernel milliseconds.  1 <= k <= 128. */
+int hb_bruteforce_ex(hb_index *ix, const void *host_queries, int64_t nq, int k, int32_t *out_elem,
+                     float *out_dist, float *dbg_scores, float *stats);
 
 /* ---- partition routing / merge -------------------------------------------------------------- */
 /* partition of a heap TID / row id: splitmix64(id) mod n_partitions */

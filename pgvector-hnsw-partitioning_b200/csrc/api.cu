@@ -170,6 +170,18 @@ dist_launch_fn get_dist_launcher(int dtype, bool ip)
 }
 
 constexpr int HB_OVERFLOW_SLOTS = 4096;
+int normalize_dev(hb_index *ix, const void *dev_in, int64_t n, void *dev_out, cudaStream_t s)
+{
+    const int wpb = 8;
+    const int grid = (int) ((n + wpb - 1) / wpb);
+    if (ix->dtype == HB_F32)
+        normalize_kernel<float><<<grid, wpb * 32, 0, s>>>((const float *) dev_in, (float *) dev_out, nullptr, n, ix->dim);
+    else
+        normalize_kernel<__half><<<grid, wpb * 32, 0, s>>>((const __half *) dev_in, (__half *) dev_out, nullptr, n, ix->dim);
+    HB_CK(cudaGetLastError());
+    return HB_OK;
+}
+
 static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 // upload n rows of dim components into the padded row layout
@@ -263,6 +275,7 @@ void hb_index_free(hb_index *ix)
 {
     if (!ix) return;
     cudaSetDevice(ix->device);
+    bruteforce_release(ix);
     cudaFree(ix->d_vecs); cudaFree(ix->d_nbr0); cudaFree(ix->d_nbr0d); cudaFree(ix->d_uoff);
     cudaFree(ix->d_nbru); cudaFree(ix->d_nbrud); cudaFree(ix->d_tid0); cudaFree(ix->d_ntids);
     cudaFree(ix->d_tidx); cudaFree(ix->d_totals);

@@ -134,6 +134,10 @@ struct DistBatchParams;
 typedef cudaError_t (*dist_launch_fn)(const DistBatchParams &, cudaStream_t);
 dist_launch_fn get_dist_launcher(int dtype, bool ip);
 
+// api.cu: canonical l2_normalize of n rows resident in HBM
+int normalize_dev(hb_index *ix, const void *dev_in, int64_t n, void *dev_out, cudaStream_t s);
+// bruteforce.cu
+void bruteforce_release(const hb_index *ix);
 // build.cu
 int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n, const int64_t *heap_tids);
 int level_for(uint64_t seed, int64_t seq, int m);

@@ -90,6 +90,7 @@ _SIGS = {
     "hb_distance_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "hb_normalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "hb_bruteforce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "hb_bruteforce_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_partition_of": (C.c_int, [C.c_int64, C.c_int]),
     "hb_partition_route": (None, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "hb_merge_topk_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -340,14 +341,22 @@ class HnswIndex:
         self._ck(self._L.hb_normalize(self._h, _p(v), v.shape[0], _p(out), _p(ok)), "hb_normalize")
         return out, ok.astype(bool)
 
-    def bruteforce(self, queries, k=10):
-        """Exact scan of the partition (recall ground truth)."""
+    def bruteforce(self, queries, k=10, debug_scores=False, stats=False):
+        """Exact scan of the partition (recall ground truth): bf16 tcgen05 GEMM candidates, fp32
+        re-rank, certified by the bf16 error bound (uncertified queries are re-scanned in fp32)."""
         q = self._vecs(queries)
         nq = q.shape[0]
         elem = np.empty((nq, k), np.int32)
         dist = np.empty((nq, k), np.float32)
-        self._ck(self._L.hb_bruteforce(self._h, _p(q), nq, k, _p(elem), _p(dist)), "hb_bruteforce")
-        return elem, dist
+        dbg = np.empty((nq, self.n), np.float32) if debug_scores else None
+        st = np.zeros(3, np.float32)
+        self._ck(self._L.hb_bruteforce_ex(self._h, _p(q), nq, k, _p(elem), _p(dist), _p(dbg), _p(st)), "hb_bruteforce")
+        out = (elem, dist)
+        if debug_scores:
+            out += (dbg,)
+        if stats:
+            out += ({"certified": int(st[0]), "rescanned": int(st[1]), "gemm_ms": float(st[2])},)
+        return out
 
 
 class HnswScan:
