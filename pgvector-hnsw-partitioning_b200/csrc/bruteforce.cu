@@ -4,21 +4,26 @@
 // is that sequential scan for a batch of queries.
 //
 //   1. candidate generation: S = Q * X^T on the 5th-gen tensor cores -- bf16 operands (TMA, 128-byte
-//      swizzle) -> tcgen05.mma, fp32 accumulators in TMEM (two 128x256 buffers) -> epilogue warps read
-//      TMEM with tcgen05.ld and keep, per query row, the K1 best columns of the slice of X this CTA
-//      streams (threshold test per score, sorted insertion only on a hit).
+//      swizzle, 4-stage mbarrier ring) -> tcgen05.mma, fp32 accumulators in TMEM (two 128x256 buffers)
+//      -> eight epilogue warps read TMEM with tcgen05.ld and keep, per query row and column half, the
+//      K1 best columns of the slice of X this CTA streams.  The selection is arranged so that it hides
+//      under the MMAs: one max + one branch per 32 columns; a hit computes its rank with independent
+//      compares and shifts a register-resident sorted list with selects; thresholds are seeded from
+//      slices of the same query that already finished (global per-query K1-th score), which cuts the
+//      insertions ~4x.
 //   2. fp32 re-rank: the exact canonical-order distance (distance.cuh) of every candidate.
 //   3. certification: bf16 rounding perturbs a dot product by at most (2^-8 + 2^-11)*|q|*|x|, so any
 //      row that was NOT kept has a true distance above a bound computed from the slice threshold; if
 //      that bound exceeds the k-th exact distance the result is provably the exact top-k.  Queries
 //      that cannot be certified are re-scanned exhaustively in fp32.
 //
-// Warp roles (192 threads, one CTA per SM, persistent over (query tile, X slice) work items):
+// Warp roles (320 threads, one CTA per SM, persistent over (query tile, X slice) work items ordered
+// slice-major so the CTAs of a wave stream the same rows of X through L2 together):
 //   warp 0 lane 0: TMA producer;  warp 1 lane 0: MMA issuer (warp 1 owns the TMEM allocation);
-//   warps 2-5: epilogue, one TMEM lane quarter each.
-// cta_group::1, M=128 N=256 K=16 per instruction.  Both operands stream from L2, which bounds this
-// single-CTA form to roughly half of the tensor peak (8192*(1/BM+1/BN) = 96 B/cycle/SM wanted);
-// pairing CTAs (cta_group::2 + multicast) is the next step and is noted in DESIGN.md.
+//   warps 2-9: epilogue, two per TMEM lane quarter.
+// cta_group::1, M=128 N=256 K=16 per instruction.  Measured on B200 at 10k x 1M x 768: the MMA/TMA
+// pipeline alone runs at 1.59 PFLOP/s; with the TMEM reads of the epilogue 1.13 PFLOP/s (0.80 of the
+// measured sustained cuBLAS peak), the selection itself no longer shows.
 #include "index.h"
 #include "scan_kernel.cuh"
 
@@ -27,24 +32,29 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
 namespace hb {
 
-constexpr int BF_BM = 128, BF_BN = 256, BF_BK = 64, BF_STAGES = 4, BF_K1 = 24, BF_K1S = 25;
-constexpr int BF_THREADS = 192;
+constexpr int BF_BM = 128, BF_BN = 256, BF_BK = 64, BF_STAGES = 4, BF_K1 = 16;
+constexpr int BF_EPI_WARPS = 8;                 // two per TMEM lane quarter, each takes half of the columns
+constexpr int BF_THREADS = 64 + 32 * BF_EPI_WARPS;
 constexpr uint32_t BF_A_BYTES = BF_BM * BF_BK * 2, BF_B_BYTES = BF_BN * BF_BK * 2;
 constexpr uint32_t BF_STAGE_BYTES = BF_A_BYTES + BF_B_BYTES;
-constexpr size_t BF_SMEM = (size_t) BF_STAGES * BF_STAGE_BYTES + (size_t) BF_BM * BF_K1S * 8 + 2 * BF_BN * 4 + 256;
+constexpr size_t BF_SMEM = (size_t) BF_STAGES * BF_STAGE_BYTES + 2 * BF_BN * 4 + 256;
 
 struct BfParams {
-    int nq, N, kchunks, n_mtiles, S, ntiles, tiles_per_split;
+    int nq, N, kchunks, n_mtiles, S, ntiles, tiles_per_split;   // candidate lists: nq x (2*S) x K1 (two column halves per slice)
     const float *xnh;        // 0.5 * |x|^2 per row for L2, nullptr for inner product / cosine
     float *cand_score;       // nq x S x K1 (bf16-GEMM scores, best first)
     int32_t *cand_id;        // nq x S x K1 (-1 padded)
     float *cand_thr;         // nq x S: score of the K1-th kept row, -inf when the slice kept everything
     float *dbg;              // optional nq x N raw scores (tests)
+    float *gthr;             // nq_pad: best K1-th score any finished slice reported for the query (threshold seed)
+    unsigned long long *ev;  // experiments: insertion events, warp-level events
+    int mode;                // experiments: 0 normal, 1 epilogue releases TMEM untouched, 2 epilogue only loads TMEM
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -115,14 +125,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void atomic_max_float(float *addr, float v)
+{
+    int old = __float_as_int(*addr);
+    while (__int_as_float(old) < v) {
+        const int assumed = old;
+        old = atomicCAS(reinterpret_cast<int *>(addr), assumed, __float_as_int(v));
+        if (old == assumed) break;
+    }
+}
+
+template <bool DBG, bool L2>
 __global__ void __launch_bounds__(BF_THREADS, 1)
 bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const BfParams p)
 {
     extern __shared__ __align__(1024) uint8_t bf_smem[];
     uint8_t *smem = bf_smem;
-    float *tk_sc = reinterpret_cast<float *>(smem + (size_t) BF_STAGES * BF_STAGE_BYTES);
-    int32_t *tk_id = reinterpret_cast<int32_t *>(tk_sc + BF_BM * BF_K1S);
-    float *xnh = reinterpret_cast<float *>(tk_id + BF_BM * BF_K1S);          // [2][BF_BN]
+    float *xnh = reinterpret_cast<float *>(smem + (size_t) BF_STAGES * BF_STAGE_BYTES);   // [2][BF_BN]
     uint64_t *full = reinterpret_cast<uint64_t *>(xnh + 2 * BF_BN);
     uint64_t *empty = full + BF_STAGES;
     uint64_t *tfull = empty + BF_STAGES;
@@ -132,7 +151,7 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < BF_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
+        for (int a = 0; a < 2; a++) { mbar_init(tfull + a, 1); mbar_init(tempty + a, BF_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -195,10 +214,9 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else {
         const int quarter = warp & 3;                         // TMEM lanes this warp may read
+        const int half = (warp - 2) >> 2;                     // which 128 of the 256 columns
         const int row = quarter * 32 + lane;
-        const int et = threadIdx.x - 64;                      // 0..127 among the epilogue threads
-        float *my_sc = tk_sc + row * BF_K1S;
-        int32_t *my_id = tk_id + row * BF_K1S;
+        const int et = threadIdx.x - 64;                      // 0..255 among the epilogue threads
         int acc = 0; uint32_t acc_phase = 0;
         const float NEG_INF = __int_as_float(0xff800000);
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -206,36 +224,90 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int nt0 = split * p.tiles_per_split, nt1 = min(nt0 + p.tiles_per_split, p.ntiles);
             const int q = m * BF_BM + row;
             const bool valid_q = q < p.nq;
-            int cnt = 0;
-            float thr = NEG_INF;
+            // the K1 best (score, column) of this query row so far: sorted, in registers.  A hit
+            // computes its rank with independent compares and shifts the tail with selects, so the
+            // rare path is ~K1 independent instructions deep instead of a K1-long dependent chain.
+            float ts[BF_K1];
+            int32_t ti[BF_K1];
+#pragma unroll
+            for (int j = 0; j < BF_K1; j++) { ts[j] = NEG_INF; ti[j] = -1; }
+            // seed: a slice that already finished for this query kept K1 rows scoring >= gthr, so rows
+            // at or below it can never reach the query's top K1 -- skip them from the start
+            const float seed = valid_q ? *reinterpret_cast<volatile float *>(p.gthr + q) : NEG_INF;
+            float thr = seed;
+            unsigned long long n_ev = 0, n_wev = 0;
             for (int nt = nt0; nt < nt1; nt++) {
                 const int n0 = nt * BF_BN;
                 float *xn = xnh + (nt & 1) * BF_BN;
-                if (p.xnh) {
-                    for (int c = et; c < BF_BN; c += 128) xn[c] = (n0 + c) < p.N ? p.xnh[n0 + c] : 0.f;
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                if constexpr (L2) {
+                    for (int c = et; c < BF_BN; c += 32 * BF_EPI_WARPS) xn[c] = (n0 + c) < p.N ? p.xnh[n0 + c] : 0.f;
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * BF_EPI_WARPS) : "memory");
                 }
                 mbar_wait(tfull + acc, acc_phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t taddr = tmem_base + ((uint32_t) (quarter * 32) << 16) + (uint32_t) acc * BF_BN;
+                const uint32_t taddr = tmem_base + ((uint32_t) (quarter * 32) << 16) + (uint32_t) acc * BF_BN + half * (BF_BN / 2);
+                const int ncols = min(BF_BN, p.N - n0);       // columns past N are TMA zero fill
 #pragma unroll 1
-                for (int c = 0; c < BF_BN / 32; c++) {
+                for (int c = 0; c < BF_BN / 64 && p.mode != 1; c++) {
                     uint32_t v[32];
                     tmem_ld32(taddr + c * 32, v);
-                    if (valid_q) {
+                    if (p.mode == 2) { if (v[lane] == 0x7fc12345u) ts[0] = 1.f; continue; }
+                    const int col0 = half * (BF_BN / 2) + c * 32;
+                    if constexpr (DBG) {
+                        if (valid_q)
+                            for (int i = 0; i < 32; i++)
+                                if (col0 + i < ncols) p.dbg[(size_t) q * p.N + n0 + col0 + i] = __uint_as_float(v[i]);
+                    }
+                    float sv[32];
 #pragma unroll
-                        for (int i = 0; i < 32; i++) {
-                            const int col = c * 32 + i;
-                            float sc = __uint_as_float(v[i]);
-                            if (p.dbg && n0 + col < p.N) p.dbg[(size_t) q * p.N + n0 + col] = sc;
-                            if (p.xnh) sc -= xn[col];
-                            if (sc > thr && n0 + col < p.N) {
-                                int j = cnt < BF_K1 ? cnt : BF_K1 - 1;
-                                if (cnt < BF_K1) cnt++;
-                                while (j > 0 && my_sc[j - 1] < sc) { my_sc[j] = my_sc[j - 1]; my_id[j] = my_id[j - 1]; j--; }
-                                my_sc[j] = sc; my_id[j] = n0 + col;
-                                if (cnt == BF_K1) thr = my_sc[BF_K1 - 1];
+                    for (int i = 0; i < 32; i++) {
+                        sv[i] = __uint_as_float(v[i]);
+                        if constexpr (L2) sv[i] -= xn[col0 + i];
+                        if (col0 + i >= ncols) sv[i] = NEG_INF;           // only the last tile of X has such columns
+                    }
+                    // one branch per 32 columns: the best of the chunk against the threshold
+                    float mx = sv[0];
+#pragma unroll
+                    for (int i = 1; i < 32; i++) mx = fmaxf(mx, sv[i]);
+                    if (p.mode == 3) n_wev += __any_sync(FULL, valid_q && mx > thr) ? 1 : 0;
+                    if (valid_q && mx > thr) {
+                        unsigned hits = 0;
+#pragma unroll
+                        for (int i = 0; i < 32; i++) hits |= sv[i] > thr ? (1u << i) : 0u;
+                        while (hits) {
+                            const int i = __ffs(hits) - 1;
+                            hits &= hits - 1;
+                            // sv[i] for a run-time i: five levels of selects keep sv in registers
+                            float m16[16], m8[8], m4[4], m2[2];
+#pragma unroll
+                            for (int t = 0; t < 16; t++) m16[t] = (i & 16) ? sv[t + 16] : sv[t];
+#pragma unroll
+                            for (int t = 0; t < 8; t++) m8[t] = (i & 8) ? m16[t + 8] : m16[t];
+#pragma unroll
+                            for (int t = 0; t < 4; t++) m4[t] = (i & 4) ? m8[t + 4] : m8[t];
+#pragma unroll
+                            for (int t = 0; t < 2; t++) m2[t] = (i & 2) ? m4[t + 2] : m4[t];
+                            const float sc = (i & 1) ? m2[1] : m2[0];
+                            if (!(sc > thr)) continue;                    // the threshold rose inside this chunk
+                            if (p.mode == 3) n_ev++;
+                            const int32_t id = n0 + col0 + i;
+                            int r0 = 0, r1 = 0, r2 = 0, r3 = 0;           // rank = entries that stay ahead (ties keep earlier columns first)
+#pragma unroll
+                            for (int j = 0; j < BF_K1; j += 4) {
+                                r0 += ts[j] >= sc ? 1 : 0;
+                                r1 += ts[j + 1] >= sc ? 1 : 0;
+                                r2 += ts[j + 2] >= sc ? 1 : 0;
+                                r3 += ts[j + 3] >= sc ? 1 : 0;
                             }
+                            const int r = (r0 + r1) + (r2 + r3);
+#pragma unroll
+                            for (int j = BF_K1 - 1; j >= 1; j--) {
+                                ts[j] = j > r ? ts[j - 1] : (j == r ? sc : ts[j]);
+                                ti[j] = j > r ? ti[j - 1] : (j == r ? id : ti[j]);
+                            }
+                            ts[0] = r == 0 ? sc : ts[0];
+                            ti[0] = r == 0 ? id : ti[0];
+                            thr = fmaxf(seed, ts[BF_K1 - 1]);
                         }
                     }
                 }
@@ -245,13 +317,13 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
+            if (p.mode == 3) { atomicAdd(p.ev, n_ev); if (lane == 0) atomicAdd(p.ev + 1, n_wev); }
             if (valid_q) {
-                const size_t o = ((size_t) q * p.S + split) * BF_K1;
-                for (int j = 0; j < BF_K1; j++) {
-                    p.cand_score[o + j] = j < cnt ? my_sc[j] : NEG_INF;
-                    p.cand_id[o + j] = j < cnt ? my_id[j] : -1;
-                }
-                p.cand_thr[(size_t) q * p.S + split] = cnt == BF_K1 ? thr : NEG_INF;
+                const size_t slot = (size_t) q * (2 * p.S) + 2 * split + half;
+#pragma unroll
+                for (int j = 0; j < BF_K1; j++) { p.cand_score[slot * BF_K1 + j] = ts[j]; p.cand_id[slot * BF_K1 + j] = ti[j]; }
+                p.cand_thr[slot] = thr;                        // every row this slice dropped scored <= thr
+                if (ti[BF_K1 - 1] >= 0) atomic_max_float(p.gthr + q, ts[BF_K1 - 1]);
             }
         }
     }
@@ -405,7 +477,7 @@ static int make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t kpad, 
 }
 
 struct BfState {
-    DevBuf xb, xnh, misc, qraw, qn, qb, qnh, cand_score, cand_id, cand_thr, cand_dist, out_elem, out_dist, uncertain, iota, full_dist, dbg;
+    DevBuf gthr, xb, xnh, misc, qraw, qn, qb, qnh, cand_score, cand_id, cand_thr, cand_dist, out_elem, out_dist, uncertain, iota, full_dist, dbg;
     int64_t built_n = -1;
     int kpad = 0;
 };
@@ -426,7 +498,7 @@ void bruteforce_release(const hb_index *ix)
     auto it = g_bf.find(ix);
     if (it == g_bf.end()) return;
     BfState *s = it->second;
-    DevBuf *b[] = { &s->xb, &s->xnh, &s->misc, &s->qraw, &s->qn, &s->qb, &s->qnh, &s->cand_score, &s->cand_id, &s->cand_thr,
+    DevBuf *b[] = { &s->gthr, &s->xb, &s->xnh, &s->misc, &s->qraw, &s->qn, &s->qb, &s->qnh, &s->cand_score, &s->cand_id, &s->cand_thr,
                     &s->cand_dist, &s->out_elem, &s->out_dist, &s->uncertain, &s->iota, &s->full_dist, &s->dbg };
     for (auto x : b) x->release();
     delete s;
@@ -514,10 +586,11 @@ int hb_bruteforce_ex(hb_index *ix, const void *host_queries, int64_t nq, int k, 
     p.S = (ntiles + p.tiles_per_split - 1) / p.tiles_per_split;
     p.ntiles = ntiles;
     p.xnh = l2 ? st.xnh.as<float>() : nullptr;
-    const size_t C = (size_t) p.S * BF_K1;
+    const int S2 = 2 * p.S;                      // two column halves per slice
+    const size_t C = (size_t) S2 * BF_K1;
     HB_CK(st.cand_score.ensure(sizeof(float) * nq * C));
     HB_CK(st.cand_id.ensure(sizeof(int32_t) * nq * C));
-    HB_CK(st.cand_thr.ensure(sizeof(float) * nq * p.S));
+    HB_CK(st.cand_thr.ensure(sizeof(float) * nq * S2));
     HB_CK(st.cand_dist.ensure(sizeof(float) * nq * C));
     HB_CK(st.out_elem.ensure(sizeof(int32_t) * nq * k));
     HB_CK(st.out_dist.ensure(sizeof(float) * nq * k));
@@ -527,16 +600,28 @@ int hb_bruteforce_ex(hb_index *ix, const void *host_queries, int64_t nq, int k, 
         HB_CK(st.dbg.ensure(sizeof(float) * nq * n));
         p.dbg = st.dbg.as<float>();
     }
+    p.mode = ix->opt_variant;   // experiment knob shared with the scan kernel
+    HB_CK(st.gthr.ensure(sizeof(float) * nq_pad));
+    {
+        std::vector<float> ninf((size_t) nq_pad, -INFINITY);
+        HB_CK(cudaMemcpyAsync(st.gthr.p, ninf.data(), sizeof(float) * nq_pad, cudaMemcpyHostToDevice, s));
+        HB_CK(cudaStreamSynchronize(s));
+    }
+    p.gthr = st.gthr.as<float>();
+    p.ev = reinterpret_cast<unsigned long long *>(max_bits + 4);
+    HB_CK(cudaMemsetAsync(p.ev, 0, 16, s));
     CUtensorMap tmA, tmB;
     int rc = make_map(&tmA, st.qb.p, (uint64_t) nq_pad, (uint64_t) kpad, BF_BM);
     if (rc) return rc;
     rc = make_map(&tmB, st.xb.p, (uint64_t) n, (uint64_t) kpad, BF_BN);
     if (rc) return rc;
-    HB_CK(cudaFuncSetAttribute(bf_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) BF_SMEM));
     const int items = p.n_mtiles * p.S;
     const int grid = std::min(items, ix->num_sms);
+    auto kern = dbg_scores ? (l2 ? bf_gemm_topk_kernel<true, true> : bf_gemm_topk_kernel<true, false>)
+                           : (l2 ? bf_gemm_topk_kernel<false, true> : bf_gemm_topk_kernel<false, false>);
+    HB_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) BF_SMEM));
     HB_CK(cudaEventRecord(ix->ev0, s));
-    bf_gemm_topk_kernel<<<grid, BF_THREADS, BF_SMEM, s>>>(tmA, tmB, p);
+    kern<<<grid, BF_THREADS, BF_SMEM, s>>>(tmA, tmB, p);
     HB_CK(cudaGetLastError());
     HB_CK(cudaEventRecord(ix->ev1, s));
 
@@ -545,7 +630,7 @@ int hb_bruteforce_ex(hb_index *ix, const void *host_queries, int64_t nq, int k, 
     dp.g = ix->view(); dp.queries = qexact; dp.nq = nq; dp.cand = st.cand_id.as<int32_t>(); dp.nc = (int) C; dp.out = st.cand_dist.as<float>();
     HB_CK(get_dist_launcher(ix->dtype, ix->metric != HB_L2)(dp, s));
     bf_select_kernel<<<(int) ((nq + 63) / 64), 64, 0, s>>>(st.cand_id.as<int32_t>(), st.cand_dist.as<float>(), st.cand_thr.as<float>(),
-                                                          st.qnh.as<float>(), max_bits, (int) nq, p.S, k, l2 ? 1 : 0,
+                                                          st.qnh.as<float>(), max_bits, (int) nq, S2, k, l2 ? 1 : 0,
                                                           st.out_elem.as<int32_t>(), st.out_dist.as<float>(), st.uncertain.as<int32_t>());
     HB_CK(cudaGetLastError());
     std::vector<int32_t> unc(nq);
@@ -577,6 +662,12 @@ int hb_bruteforce_ex(hb_index *ix, const void *host_queries, int64_t nq, int k, 
             HB_CK(cudaMemcpyAsync(out_dist + q * k, st.out_dist.as<float>() + q * k, sizeof(float) * k, cudaMemcpyDeviceToHost, s));
         }
         HB_CK(cudaStreamSynchronize(s));
+    }
+    if (p.mode == 3) {
+        unsigned long long ev[2];
+        cudaMemcpy(ev, p.ev, 16, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[bf] insertion events %llu (%.1f per thread-item), warp-level events %llu, columns per thread-item %d, S=%d\n", ev[0],
+                (double) ev[0] / ((double) nq * 2 * p.S), ev[1], p.tiles_per_split * BF_BN / 2, p.S);
     }
     if (stats) { stats[0] = (float) (nq - n_unc); stats[1] = (float) n_unc; stats[2] = gemm_ms; }
     return HB_OK;
