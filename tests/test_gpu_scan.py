@@ -207,14 +207,14 @@ def test_many_exact_ties(oracle, pkg):
 
 
 def test_tie_tail_overflow_uses_long_list_path(oracle, pkg):
-    """all points of the {0,1}^10 lattice: 45 (120, 210 ...) distinct elements tie exactly at the ef
-    boundary, more than the shared-memory tie tail holds, so those queries re-run on the long-list /
-    bitmap path."""
+    """all points of the {0,1}^12 lattice: dozens of distinct elements tie exactly at the ef boundary;
+    with ef=64 more than 16 of them are pushed past position ef (21 in a host emulation), which the
+    shared-memory tie tail cannot hold, so those queries re-run on the long-list / bitmap path."""
     rng = np.random.default_rng(6)
-    x = np.array([[(i >> b) & 1 for b in range(10)] for i in range(1024)], np.float32)[rng.permutation(1024)]
-    q = x[rng.integers(0, 1024, 60)]
+    x = np.array([[(i >> b) & 1 for b in range(12)] for i in range(4096)], np.float32)[rng.permutation(4096)]
+    q = x[rng.integers(0, 4096, 60)]
     orc, ix = make(oracle, pkg, x, oracle.L2, m=8, efc=32)
-    c = check_scan(oracle, orc, ix, q, 10, natural_check=False)
+    c = check_scan(oracle, orc, ix, q, 64, natural_check=False)
     assert c["n_slow"] > 0
     ix.close()
 
