@@ -157,9 +157,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "partitioned"])
-    ap.add_argument("--n", type=int, default=1000000)
+    ap.add_argument("--rows", dest="n", type=int, default=1000000)
     ap.add_argument("--dim", type=int, default=768)
-    ap.add_argument("--nq", type=int, default=10000)
+    ap.add_argument("--queries", dest="nq", type=int, default=10000)
     ap.add_argument("--ef", type=int, default=0, help="hnsw.ef_search (0 = smallest of the sweep reaching recall 0.95)")
     ap.add_argument("--partitions", type=int, default=8)
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = sized for ~15 s)")

@@ -289,3 +289,36 @@ def test_merge_topk(pkg):
     for i in range(nq):
         allp = sorted((d[p, i, j], p, t[p, i, j]) for p in range(P) for j in range(k) if t[p, i, j] >= 0)[:k]
         assert [a[2] for a in allp] == ot[i].tolist()
+
+
+def test_c1_config_on_gpu_built_graph(oracle, pkg):
+    """configs[0] (the reference's own CPU-runnable case): 100k x 128 SIFT-shaped L2, m=16,
+    ef_construction=64, ef_search=40, k=10, one partition.  The graph is built on the GPU (the
+    single-threaded oracle build of 100k rows takes minutes); the oracle then searches that same graph
+    on the CPU and must return the same ids, distances and counters."""
+    n, nq = 100000, 1000
+    x = sift_like(n, 128, seed=21)
+    q = sift_like(nq, 128, seed=22)
+    ix = pkg.HnswIndex(128, "vector_l2_ops", 16, 64, capacity=n, seed=3)
+    assert ix.build(x) == n
+    orc = oracle.Index.from_graph(ix.export_graph())
+    check_scan(oracle, orc, ix, q, 40)
+    gt, _ = ix.bruteforce(q, 10)
+    elem, _, _ = ix.search_elements(q, 40)
+    rec = np.mean([len(set(elem[i, :10]) & set(gt[i])) / 10 for i in range(nq)])
+    assert rec >= 0.9, rec
+    ix.close()
+
+
+@pytest.mark.parametrize("dim,dtype,m,ef", [(2000, 0, 8, 20), (4000, 1, 8, 20), (16, 0, 100, 300), (32, 0, 16, 1000), (64, 1, 16, 500)])
+def test_limits(oracle, pkg, dim, dtype, m, ef):
+    """pgvector's limits: 2000 dims (vector) / 4000 (halfvec) in hnsw, m = 100, ef_search = 1000."""
+    dt = np.float16 if dtype else np.float32
+    x = clustered(1200, dim, 8, seed=dim, dtype=dt)
+    q = clustered(40, dim, 8, seed=dim + 1, dtype=dt)
+    orc, ix = make(oracle, pkg, x, oracle.L2, dtype=dtype, m=m, efc=max(2 * m, 32))
+    check_scan(oracle, orc, ix, q, ef, natural_check=False)
+    ix.close()
+    with pytest.raises(pkg.HnswError):
+        ix2 = pkg.HnswIndex(8, "vector_l2_ops", 8, 32, capacity=10)
+        ix2.search(np.zeros((1, 8), np.float32), 5, 1001)       # hnsw.ef_search is capped at 1000
