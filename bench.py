@@ -252,7 +252,7 @@ def main():
     # ---------------------------------------------------------------- device-resident steps
     # Steps alternate between two CUDA streams (each with its own output buffers), the way a server
     # keeps two batches in flight: the drain of one batch overlaps the ramp of the next.
-    NSTREAM = 2
+    NSTREAM = 3
     streams = [torch.cuda.Stream(device=dev) for _ in range(NSTREAM)]
     outs = [(torch.empty((nq, ef), dtype=torch.int32, device=dev), torch.empty((nq, ef), dtype=torch.float32, device=dev),
              torch.empty((nq,), dtype=torch.int32, device=dev)) for _ in range(NSTREAM)]
@@ -343,7 +343,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: %dx%d fp32 cosine, m=16, ef_construction=64, ef_search=%d, k=10, batch=%d "
-                                   "queries/step resident in HBM, steps alternate on 2 streams%s" % (n, dim, ef, nq, "" if world == 1 else ", one replica per GPU (replicas only)"),
+                                   "queries/step resident in HBM, steps rotate over 3 streams%s" % (n, dim, ef, nq, "" if world == 1 else ", one replica per GPU (replicas only)"),
                        "ef_search": ef, "recall@10": round(rec, 4), "recall_sweep": sweep, "parallelism": "replicas x%d" % world,
                        "l2_policy": "inputs larger than L2: graph+vectors %.2f GB, a distinct query batch every step" % ((n * row_bytes + n * 128) / 1e9),
                        "parity": "unpinned (reference mount has no source); ids bit-identical to oracle/ in tests"},

@@ -421,13 +421,19 @@ int64_t hb_insert(hb_index *ix, const void *host_vecs, int64_t n, const int64_t 
 // ---- scan ------------------------------------------------------------------------------------
 static int choose_slots(const hb_index *ix, int ef, int capW)
 {
-    // ~5-12 distance evaluations per unit of ef is typical; heavier queries spill into the per-warp
-    // overflow table in HBM
-    int slots = ix->opt_slots > 0 ? pow2ceil(ix->opt_slots) : pow2ceil(ef * 16);
-    if (ix->opt_slots <= 0 && slots < 1024) slots = 1024;
+    // ~5-15 distance evaluations per unit of ef is typical.  At least 16*ef slots; more (up to 64*ef)
+    // while a warp's shared memory stays within ~12 kB, so that 16 warps fit an SM; heavier queries
+    // spill into the per-warp overflow table in HBM.
+    const size_t fixed = (size_t) ix->nvec * (ix->dtype == HB_F32 ? 4 : 8) * 4 + (size_t) capW * 8 + 16;
+    int slots;
+    if (ix->opt_slots > 0) slots = pow2ceil(ix->opt_slots);
+    else {
+        slots = std::max(1024, pow2ceil(ef * 16));
+        const int cap = pow2ceil(ef * 64);
+        while (slots < cap && fixed + (size_t) slots * 2 * 4 <= 12288) slots <<= 1;
+    }
     if (slots < 64) slots = 64;
     // keep SCAN_WARPS warps within 200 kB of shared memory
-    const size_t fixed = (size_t) ix->nvec * (ix->dtype == HB_F32 ? 4 : 8) * 4 + (size_t) capW * 8 + 16;
     while (slots > 256 && (fixed + (size_t) slots * 4) * SCAN_WARPS > 200 * 1024) slots >>= 1;
     return slots;
 }

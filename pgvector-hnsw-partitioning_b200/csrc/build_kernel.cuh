@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_search_kernel(const Bu
         if (item >= total) break;
         const int i = p.qlist ? p.qlist[item] : (int) item;
         __syncwarp();
-        stage_query<T>(reinterpret_cast<const T *>(g.vecs + (size_t) (p.first + i) * g.row_bytes), g.dim, g.nvec, q, lane);
+        stage_row<T>(g.vecs + (size_t) (p.first + i) * g.row_bytes, g.nvec, q, lane);
         __syncwarp();
 
         QueryCounters ctr = { 0, 0, 0 };
@@ -160,7 +160,7 @@ __device__ __forceinline__ int select_neighbors_warp(const GraphView &g, float *
         bool closer = true;
         if (nr > 0) {
             __syncwarp();
-            stage_query<T>(reinterpret_cast<const T *>(g.vecs + (size_t) e * g.row_bytes), g.dim, g.nvec, q, lane);
+            stage_row<T>(g.vecs + (size_t) e * g.row_bytes, g.nvec, q, lane);
             __syncwarp();
             // CheckElementCloser: rejected as soon as one selected neighbour is at least as close
             // to e as the owner is; evaluated eight selected neighbours at a time
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) nbr_dist_kernel(const NbrDis
     for (int64_t row = (int64_t) blockIdx.x * BUILD_WARPS + warp; row < p.rows; row += (int64_t) gridDim.x * BUILD_WARPS) {
         const int64_t owner = p.owner_of_row ? p.owner_of_row[row] : row;
         __syncwarp();
-        stage_query<T>(reinterpret_cast<const T *>(g.vecs + (size_t) owner * g.row_bytes), g.dim, g.nvec, q, lane);
+        stage_row<T>(g.vecs + (size_t) owner * g.row_bytes, g.nvec, q, lane);
         __syncwarp();
         for (int jb = 0; jb < p.deg; jb += 32) {
             const int j = jb + lane;

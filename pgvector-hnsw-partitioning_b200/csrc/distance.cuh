@@ -205,4 +205,24 @@ __device__ __forceinline__ void stage_query(const T *__restrict__ src, int dim, 
     }
 }
 
+// stage a row that lives in the index (padded to whole 16-byte chunks, 16-byte aligned) as the query:
+// 128-bit loads, same shared-memory layout as stage_query
+template <typename T>
+__device__ __forceinline__ void stage_row(const char *__restrict__ row, int nvec, float *q, int lane)
+{
+    for (int ch = lane; ch < nvec; ch += 32) {
+        const uint4 raw = *reinterpret_cast<const uint4 *>(row + 16 * ch);
+        if constexpr (sizeof(T) == 4) {
+            *reinterpret_cast<uint4 *>(q + 4 * ch) = raw;
+        } else {
+            const float2 h0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+            const float2 h1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+            const float2 h2 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.z));
+            const float2 h3 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.w));
+            *reinterpret_cast<float4 *>(q + 4 * ch) = make_float4(h0.x, h0.y, h1.x, h1.y);
+            *reinterpret_cast<float4 *>(q + 4 * nvec + 4 * ch) = make_float4(h2.x, h2.y, h3.x, h3.y);
+        }
+    }
+}
+
 }   // namespace hb
