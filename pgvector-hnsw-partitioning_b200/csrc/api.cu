@@ -279,6 +279,7 @@ void hb_index_free(hb_index *ix)
     cudaFree(ix->d_vecs); cudaFree(ix->d_nbr0); cudaFree(ix->d_nbr0d); cudaFree(ix->d_uoff);
     cudaFree(ix->d_nbru); cudaFree(ix->d_nbrud); cudaFree(ix->d_tid0); cudaFree(ix->d_ntids);
     cudaFree(ix->d_tidx); cudaFree(ix->d_totals);
+    hb::release_pair_cache(ix);
     hb::DevBuf *bufs[] = { &ix->ws_q, &ix->ws_qn, &ix->ws_elem, &ix->ws_dist, &ix->ws_status, &ix->ws_misc,
                            &ix->ws_gbits, &ix->ws_gwd, &ix->ws_gwi, &ix->ws_ovf };
     for (auto b : bufs) b->release();
@@ -286,6 +287,7 @@ void hb_index_free(hb_index *ix)
     for (auto &kv : ix->stream_ws) { kv.second->release(); delete kv.second; }
     ix->stream_ws.clear();
     for (auto &b : ix->ws_build) b.release();
+    if (ix->h_flag) cudaFreeHost(ix->h_flag);
     if (ix->ev0) cudaEventDestroy(ix->ev0);
     if (ix->ev1) cudaEventDestroy(ix->ev1);
     if (ix->stream) cudaStreamDestroy(ix->stream);
@@ -311,6 +313,8 @@ int hb_set_option(hb_index *ix, const char *name, int value)
     else if (!strcmp(name, "build_batch")) ix->opt_build_batch = value;
     else if (!strcmp(name, "per_query_counters")) ix->opt_per_query = value;
     else if (!strcmp(name, "variant")) ix->opt_variant = value;
+    else if (!strcmp(name, "link_kernel")) ix->opt_link_kernel = value;
+    else if (!strcmp(name, "pair_cache")) ix->opt_pair_cache = value;
     else { set_error("hb_set_option: unknown option %s", name); return HB_EINVAL; }
     return HB_OK;
 }
@@ -380,6 +384,7 @@ int hb_index_load(hb_index *ix, int64_t n, int64_t upper_rows, int32_t entry, co
     // cached neighbour distances are unknown for a loaded graph; build.cu recomputes on demand
     if (ix->d_nbr0d) { cudaFree(ix->d_nbr0d); ix->d_nbr0d = nullptr; }
     if (ix->d_nbrud) { cudaFree(ix->d_nbrud); ix->d_nbrud = nullptr; }
+    hb::release_pair_cache(ix);
     HB_CK(cudaDeviceSynchronize());
     return sync_tids_to_device(ix, 0, n);
 }

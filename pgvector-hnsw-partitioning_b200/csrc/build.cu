@@ -2,16 +2,25 @@
 // UpdateGraphInMemory / UpdateNeighborsInMemory, hnswutils.c HnswFindElementNeighbors
 // [RECALL; reference mount empty, /root/reference/README.md:1]).
 //
-// Per batch:  upload rows -> build_search_kernel (candidates per layer) -> build_select_kernel
-// (heuristic selection + duplicate detection) -> host: fold duplicates into existing elements,
-// assign ids, group reverse links by (layer, target) -> build_commit_kernel (AddConnections) ->
-// build_link_kernel (HnswUpdateConnection).  The host only moves bookkeeping integers; every
-// distance is evaluated on the GPU.  A batch is at most 1/16 of the current graph, and an element
-// that would raise the entry level is inserted alone.
+// Per batch, all on one stream with no host round trip in between:
+//   upload rows -> build_search_kernel (candidates per layer) -> build_select_kernel (heuristic
+//   selection + duplicate detection) -> build_check_kernel -> build_commit_kernel (AddConnections)
+//   -> edge_gen_kernel (reverse links as sortable keys) -> radix sort by (layer, target, source)
+//   -> seg_heads_kernel -> link kernel (HnswUpdateConnection, link_kernel.cuh).
+// The host assumes the batch holds no duplicate of an indexed vector (ids = arrival order) and
+// reads one flag word back per batch; when the check kernel found a duplicate the kernels after it
+// did nothing, the host folds the duplicates (FindDuplicateInMemory, <= 10 heap TIDs per element),
+// renumbers and re-runs the tail.  The host only moves bookkeeping integers; every distance is
+// evaluated on the GPU.  A batch is at most 1/16 of the current graph, and an element that would
+// raise the entry level is inserted alone.
 #include "index.h"
 #include "build_kernel.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <tuple>
 
@@ -20,7 +29,7 @@ namespace hb {
 #define HB_DECLB(name)                                                                                   \
     cudaError_t build_search_##name(const BuildSearchParams &, int, int, cudaStream_t, bool slow);       \
     cudaError_t build_select_##name(const BuildSelectParams &, int, cudaStream_t);                       \
-    cudaError_t build_link_##name(const BuildLinkParams &, int, cudaStream_t);                           \
+    cudaError_t build_link_##name(const LinkParams &, int, int, cudaStream_t);                           \
     cudaError_t nbr_dist_##name(const NbrDistParams &, int, cudaStream_t);
 HB_DECLB(f32_l2) HB_DECLB(f32_ip) HB_DECLB(f16_l2) HB_DECLB(f16_ip)
 #undef HB_DECLB
@@ -74,8 +83,41 @@ __global__ void normalize_rows_kernel(const T *__restrict__ in, char *__restrict
     }
 }
 
+void release_pair_cache(hb_index *ix)
+{
+    cudaFree(ix->d_pc0); cudaFree(ix->d_pcu); cudaFree(ix->d_pv0); cudaFree(ix->d_pvu);
+    ix->d_pc0 = ix->d_pcu = nullptr; ix->d_pv0 = ix->d_pvu = nullptr;
+    ix->pair_cache_tried = false;
+}
+
+// the pair cache costs lm0(lm0-1)/2 floats per element (2 kB at m = 16): taken only when it fits in a
+// third of the free memory
+static int ensure_pair_cache(hb_index *ix)
+{
+    if (ix->pair_cache_tried) return HB_OK;
+    ix->pair_cache_tried = true;
+    const int lm0 = 2 * ix->m;
+    if (!ix->opt_pair_cache || lm0 > LINK_MAX_LM) return HB_OK;
+    const size_t b0 = sizeof(float) * (size_t) ix->cap * (lm0 * (lm0 - 1) / 2);
+    const size_t bu = sizeof(float) * (size_t) ix->upper_cap * (ix->m * (ix->m - 1) / 2);
+    size_t free_b = 0, total_b = 0;
+    HB_CK(cudaMemGetInfo(&free_b, &total_b));
+    if (b0 + bu > free_b / 3) return HB_OK;
+    HB_CK(cudaMalloc(&ix->d_pc0, b0));
+    HB_CK(cudaMalloc(&ix->d_pcu, bu));
+    HB_CK(cudaMalloc(&ix->d_pv0, ix->cap));
+    HB_CK(cudaMalloc(&ix->d_pvu, ix->upper_cap));
+    HB_CK(cudaMemset(ix->d_pv0, 0, ix->cap));
+    HB_CK(cudaMemset(ix->d_pvu, 0, ix->upper_cap));
+    return HB_OK;
+}
+
 static int ensure_build_arrays(hb_index *ix, cudaStream_t s)
 {
+    {
+        const int rc = ensure_pair_cache(ix);
+        if (rc) return rc;
+    }
     if (ix->d_nbr0d) return HB_OK;
     const int m2 = 2 * ix->m;
     HB_CK(cudaMalloc(&ix->d_nbr0d, sizeof(float) * ix->cap * m2));
@@ -114,7 +156,122 @@ static bool all_zero(const char *row, size_t bytes, int esize)
     return true;
 }
 
-struct Edge { int32_t layer, target, src; float d; };
+// ---- small kernels of the batch tail (no distances here) ---------------------------------------
+// flag bit 0: an insert hit the tie limit (error); bit 1: a new row is byte-identical to a neighbour
+static __global__ void build_check_kernel(const int32_t *__restrict__ status, const int32_t *__restrict__ dup, int B,
+                                          int32_t *flag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    int f = 0;
+    if (status[i] < 0) f |= 1;
+    if (dup[(size_t) i * DUP_SLOTS] >= 0) f |= 2;
+    if (f) atomicOr(flag, f);
+}
+
+constexpr int BUILD_SLOW_GRID = 16;
+
+struct EdgeGenParams {
+    int B, UR, m;
+    int64_t first;
+    const int32_t *final_id;        // B
+    const int32_t *urow_owner;      // UR: batch index of the element owning upper candidate row r
+    const int32_t *urow_layer;      // UR
+    const int32_t *sel0_id; const float *sel0_d; const int32_t *sel0_cnt;
+    const int32_t *selu_id; const float *selu_d; const int32_t *selu_cnt;
+    unsigned long long *key; float *val;
+    const int32_t *flag;
+};
+
+// one thread per selected-neighbour slot: the reverse link (layer, target = neighbour, source = new element)
+static __global__ void edge_gen_kernel(const EdgeGenParams p)
+{
+    if (*p.flag) return;
+    const int lm0 = 2 * p.m;
+    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n0 = (int64_t) p.B * lm0, total = n0 + (int64_t) p.UR * p.m;
+    if (t >= total) return;
+    unsigned long long key = LINK_KEY_INVALID;
+    float d = 0.f;
+    if (t < n0) {
+        const int i = (int) (t / lm0), j = (int) (t % lm0);
+        const int32_t f = p.final_id[i];
+        if (f >= 0 && j < p.sel0_cnt[i]) {
+            key = ((unsigned long long) (uint32_t) p.sel0_id[t] << LINK_KEY_SRC_BITS) | (unsigned long long) (f - p.first);
+            d = p.sel0_d[t];
+        }
+    } else {
+        const int64_t u = t - n0;
+        const int r = (int) (u / p.m), j = (int) (u % p.m);
+        const int32_t f = p.final_id[p.urow_owner[r]];
+        if (f >= 0 && j < p.selu_cnt[r]) {
+            key = ((unsigned long long) p.urow_layer[r] << (32 + LINK_KEY_SRC_BITS)) |
+                  ((unsigned long long) (uint32_t) p.selu_id[u] << LINK_KEY_SRC_BITS) | (unsigned long long) (f - p.first);
+            d = p.selu_d[u];
+        }
+    }
+    p.key[t] = key;
+    p.val[t] = d;
+}
+
+// segment = run of sorted edges with the same (layer, target); order of the segment list is free
+static __global__ void seg_heads_kernel(const unsigned long long *__restrict__ key, int E, int32_t *seg_start,
+                                        int32_t *nseg, const int32_t *flag)
+{
+    if (*flag) return;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const unsigned long long k = key[e];
+    if (k == LINK_KEY_INVALID) return;
+    if (e + 1 == E || key[e + 1] == LINK_KEY_INVALID) nseg[1] = e + 1;      // number of valid edges
+    if (e == 0 || (key[e - 1] >> LINK_KEY_SRC_BITS) != (k >> LINK_KEY_SRC_BITS)) seg_start[atomicAdd(nseg, 1)] = e;
+}
+
+// AddConnections plus the per-element words of the new elements (uoff, first heap TID)
+struct CommitParams {
+    int B, UR, m;
+    const int32_t *final_id;      // B: element id, or -1 for a tuple folded into a duplicate
+    const int32_t *new_uoff;      // B
+    const int64_t *tid;           // B
+    const int32_t *dest_urow;     // UR: row in nbru, or -1
+    const int32_t *sel0_id; const float *sel0_d;
+    const int32_t *selu_id; const float *selu_d;
+    int32_t *nbr0; float *nbr0d; int32_t *nbru; float *nbrud;
+    int32_t *uoff; int64_t *tid0; uint8_t *ntids;
+    uint8_t *pv0, *pvu;           // pair-cache filled flags (NULL without the cache): new lists start unfilled
+    const int32_t *flag;
+};
+
+static __global__ void build_commit_kernel(const CommitParams p)
+{
+    if (*p.flag) return;
+    const int lm0 = 2 * p.m;
+    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n0 = (int64_t) p.B * lm0;
+    if (t < n0) {
+        const int i = (int) (t / lm0), j = (int) (t % lm0);
+        const int32_t f = p.final_id[i];
+        if (f >= 0) {
+            p.nbr0[(size_t) f * lm0 + j] = p.sel0_id[t]; p.nbr0d[(size_t) f * lm0 + j] = p.sel0_d[t];
+            if (j == 0) { p.uoff[f] = p.new_uoff[i]; p.tid0[f] = p.tid[i]; p.ntids[f] = 1; if (p.pv0) p.pv0[f] = 0; }
+        }
+    } else if (t < n0 + (int64_t) p.UR * p.m) {
+        const int64_t u = t - n0;
+        const int r = (int) (u / p.m), j = (int) (u % p.m);
+        const int32_t dr = p.dest_urow[r];
+        if (dr >= 0) {
+            p.nbru[(size_t) dr * p.m + j] = p.selu_id[u]; p.nbrud[(size_t) dr * p.m + j] = p.selu_d[u];
+            if (j == 0 && p.pvu) p.pvu[dr] = 0;
+        }
+    }
+}
+
+template <typename V> static inline V *carve(char *&p, size_t count)
+{
+    V *r = reinterpret_cast<V *>(p);
+    p += (count * sizeof(V) + 15) & ~(size_t) 15;
+    return r;
+}
 
 int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const int64_t *heap_tids)
 {
@@ -123,8 +280,6 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
     cudaStream_t s = ix->stream;
     const size_t src_row = (size_t) ix->dim * ix->esize;
     const int m = ix->m, m2 = 2 * m, efc = ix->efc;
-    const bool ip = ix->metric != HB_L2;
-    (void) ip;
 
     // tuples to index, in order (HnswCheckNorm drops zero-norm vectors under the cosine opclass)
     std::vector<int64_t> todo;
@@ -142,19 +297,58 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
     ix->h_level.reserve(ix->n + todo.size());
     ix->h_ntids.reserve(ix->n + todo.size());
     ix->h_tids.reserve((ix->n + todo.size()) * HB_HEAPTIDS);
+    if (!ix->h_flag) HB_CK(cudaMallocHost(&ix->h_flag, 16));
 
-    const int max_batch = ix->opt_build_batch > 0 ? ix->opt_build_batch : 4096;
+    // HB_BUILD_TRACE=1: where the host's wall time goes (enqueue vs waiting for the device)
+    const bool trace = getenv("HB_BUILD_TRACE") != nullptr;
+    double t_prep = 0, t_wait = 0, t_post = 0;
+    int64_t n_batches = 0, n_segs = 0, n_edges = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    cudaEvent_t tev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    double t_dev[4] = { 0, 0, 0, 0 };   // upload+search | select | commit+edges+sort | link
+    if (trace) for (auto &e : tev) HB_CK(cudaEventCreate(&e));
+
+    const int max_batch = std::min(ix->opt_build_batch > 0 ? ix->opt_build_batch : 4096, 1 << LINK_KEY_SRC_BITS);
     int64_t indexed = 0;
     size_t pos = 0;
-    std::vector<char> stage;
+    std::vector<char> stage, pack;
     std::vector<uint8_t> levels;
-    std::vector<int32_t> ucand_row, final_id, dest_urow, sel0_id, sel0_cnt, selu_id, selu_cnt, dup, status, new_uoff;
-    std::vector<float> sel0_d, selu_d;
-    std::vector<Edge> edges;
-    std::vector<int32_t> seg_off, seg_target, seg_layer, edge_src;
-    std::vector<float> edge_d;
+    std::vector<int32_t> ucand_row, dup;
+
+    // workspaces are sized once for the largest batch this call can form (cudaFree inside the
+    // loop would stall the pipeline); a batch with unusually many upper-layer rows regrows them
+    auto size_workspaces = [&](int64_t b, int64_t UR1) -> int {
+        hb::DevBuf *W = ix->ws_build;
+        const int64_t E = b * m2 + UR1 * m;
+        HB_CK(W[1].ensure(((size_t) 3 * b + 3 * UR1) * 4 + (size_t) b * 9 + 256));   // packed bookkeeping words
+        HB_CK(W[3].ensure((size_t) b * efc * 8 + sizeof(int32_t) * b));       // cand0 id | d | cnt
+        HB_CK(W[4].ensure((size_t) UR1 * efc * 8 + sizeof(int32_t) * UR1));
+        HB_CK(W[5].ensure((size_t) b * m2 * 8 + sizeof(int32_t) * b));        // sel0 id | d | cnt
+        HB_CK(W[6].ensure((size_t) UR1 * m * 8 + sizeof(int32_t) * UR1));     // selu id | d | cnt
+        HB_CK(W[7].ensure(sizeof(int32_t) * b * DUP_SLOTS));
+        HB_CK(W[8].ensure(sizeof(int32_t) * b * 2 + 64));                     // status | slow list
+        HB_CK(W[9].ensure((size_t) E * (8 + 8 + 4 + 4 + 4) + 128));           // keys in/out | vals in/out | seg_start
+        if (ix->metric == HB_COSINE) HB_CK(ix->ws_build[0].ensure((size_t) b * src_row));
+        HB_CK(ix->ws_misc.ensure(256));
+        return HB_OK;
+    };
+    {
+        const int64_t bmax = std::min<int64_t>(max_batch, std::max<int64_t>(1, std::min<int64_t>((int64_t) todo.size(), (ix->n + (int64_t) todo.size()) / 16)));
+        rc = size_workspaces(bmax, std::max<int64_t>(bmax / 4, 64));
+        if (rc) return rc;
+        size_t sort_bytes = 0;
+        HB_CK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (unsigned long long *) nullptr, (unsigned long long *) nullptr,
+                                              (float *) nullptr, (float *) nullptr, (int) (bmax * m2 + std::max<int64_t>(bmax / 4, 64) * m), 0, 64, s));
+        HB_CK(ix->ws_build[10].ensure(sort_bytes + 16));
+        // large-visited-set path of the candidate search: bitmaps sized for the final graph
+        const int64_t slow_warps = (int64_t) BUILD_SLOW_GRID * BUILD_WARPS;
+        HB_CK(ix->ws_gbits.ensure(sizeof(uint32_t) * slow_warps * ((ix->n + (int64_t) todo.size() + 31) / 32 + 2)));
+    }
 
     while (pos < todo.size()) {
+        const double t0 = now();
+        n_batches++;
         const int64_t cur = ix->n;
         int64_t b = std::max<int64_t>(1, std::min<int64_t>(max_batch, cur / 16));
         b = std::min<int64_t>(b, (int64_t) todo.size() - pos);
@@ -168,12 +362,15 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         levels.resize(b);
 
         // ---- rows into HBM at [cur, cur + b)
-        stage.resize((size_t) b * src_row);
-        for (int64_t i = 0; i < b; i++) memcpy(&stage[i * src_row], (const char *) host_vecs + todo[pos + i] * src_row, src_row);
+        const char *src = (const char *) host_vecs + todo[pos] * src_row;
+        if (todo[pos + b - 1] - todo[pos] != b - 1) {       // a zero vector was skipped inside the batch
+            stage.resize((size_t) b * src_row);
+            for (int64_t i = 0; i < b; i++) memcpy(&stage[i * src_row], (const char *) host_vecs + todo[pos + i] * src_row, src_row);
+            src = stage.data();
+        }
         char *rows = ix->d_vecs + (size_t) cur * ix->row_bytes;
         if (ix->metric == HB_COSINE) {
-            HB_CK(ix->ws_build[0].ensure((size_t) b * src_row));
-            HB_CK(cudaMemcpyAsync(ix->ws_build[0].p, stage.data(), (size_t) b * src_row, cudaMemcpyHostToDevice, s));
+            HB_CK(cudaMemcpyAsync(ix->ws_build[0].p, src, (size_t) b * src_row, cudaMemcpyHostToDevice, s));
             const int wpb = 8, grid = (int) ((b + wpb - 1) / wpb);
             if (ix->dtype == HB_F32)
                 normalize_rows_kernel<float><<<grid, wpb * 32, 0, s>>>(ix->ws_build[0].as<float>(), rows, ix->row_bytes, b, ix->dim);
@@ -181,10 +378,10 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
                 normalize_rows_kernel<__half><<<grid, wpb * 32, 0, s>>>(ix->ws_build[0].as<__half>(), rows, ix->row_bytes, b, ix->dim);
             HB_CK(cudaGetLastError());
         } else if (src_row == ix->row_bytes) {
-            HB_CK(cudaMemcpyAsync(rows, stage.data(), src_row * b, cudaMemcpyHostToDevice, s));
+            HB_CK(cudaMemcpyAsync(rows, src, src_row * b, cudaMemcpyHostToDevice, s));
         } else {
             HB_CK(cudaMemsetAsync(rows, 0, ix->row_bytes * b, s));
-            HB_CK(cudaMemcpy2DAsync(rows, ix->row_bytes, stage.data(), src_row, src_row, b, cudaMemcpyHostToDevice, s));
+            HB_CK(cudaMemcpy2DAsync(rows, ix->row_bytes, src, src_row, src_row, b, cudaMemcpyHostToDevice, s));
         }
 
         auto tid_of = [&](int64_t i) { return heap_tids ? heap_tids[todo[pos + i]] : todo[pos + i]; };
@@ -204,6 +401,8 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
             // stale lists from a previous life of this slot
             HB_CK(cudaMemset(ix->d_nbr0, 0xff, sizeof(int32_t) * m2));
             if (lv > 0) HB_CK(cudaMemset(ix->d_nbru, 0xff, sizeof(int32_t) * (size_t) lv * m));
+            if (ix->d_pv0) HB_CK(cudaMemset(ix->d_pv0, 0, 1));
+            if (ix->d_pvu && lv > 0) HB_CK(cudaMemset(ix->d_pvu, 0, lv));
             // heap TIDs of the first element
             {
                 int64_t t0 = ix->h_tids[0];
@@ -215,7 +414,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
             continue;
         }
 
-        // ---- candidate search
+        // ---- the batch's bookkeeping integers, assuming no tuple folds into a duplicate
         const int EL = ix->entry_level;
         ucand_row.assign(b, -1);
         int UR = 0;
@@ -223,27 +422,65 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
             const int l = std::min<int>(levels[i], EL);
             if (l > 0) { ucand_row[i] = UR; UR += l; }
         }
-        hb::DevBuf *W = ix->ws_build;
-        HB_CK(W[1].ensure(b));                                           // level
-        HB_CK(W[2].ensure(sizeof(int32_t) * b * 3));                     // ucand_row | final_id | new uoff
-        HB_CK(W[3].ensure((size_t) b * efc * 8 + sizeof(int32_t) * b));  // cand0 id | d | cnt
-        HB_CK(W[4].ensure((size_t) std::max(UR, 1) * efc * 8 + sizeof(int32_t) * std::max(UR, 1)));
-        HB_CK(W[5].ensure((size_t) b * m2 * 8 + sizeof(int32_t) * b));   // sel0 id | d | cnt
-        HB_CK(W[6].ensure((size_t) std::max(UR, 1) * m * 8 + sizeof(int32_t) * std::max(UR, 1) * 2));   // selu id | d | cnt | dest_urow
-        HB_CK(W[7].ensure(sizeof(int32_t) * b * DUP_SLOTS));
-        HB_CK(W[8].ensure(sizeof(int32_t) * b * 2 + 64));                // status | slow list
-        HB_CK(ix->ws_misc.ensure(256));
-        HB_CK(cudaMemcpyAsync(W[1].p, levels.data(), b, cudaMemcpyHostToDevice, s));
-        HB_CK(cudaMemcpyAsync(W[2].p, ucand_row.data(), sizeof(int32_t) * b, cudaMemcpyHostToDevice, s));
-        unsigned int *misc = ix->ws_misc.as<unsigned int>();
-        HB_CK(cudaMemsetAsync(misc, 0, 16, s));
+        const int UR1 = std::max(UR, 1);
+        // host image of the packed words: ucand_row | final_id | new_uoff | dest_urow | urow_owner | urow_layer | tid | level
+        const size_t pack_bytes = ((size_t) 3 * b + 3 * UR1) * 4 + 64 + (size_t) b * 8 + b + 16 * 8;
+        pack.assign(pack_bytes, 0);
+        char *hp = pack.data();
+        int32_t *h_ucand = carve<int32_t>(hp, b);
+        int32_t *h_final = carve<int32_t>(hp, b);
+        int32_t *h_nuoff = carve<int32_t>(hp, b);
+        int32_t *h_durow = carve<int32_t>(hp, UR1);
+        int32_t *h_uown = carve<int32_t>(hp, UR1);
+        int32_t *h_ulay = carve<int32_t>(hp, UR1);
+        int64_t *h_tid = carve<int64_t>(hp, b);
+        uint8_t *h_lev = carve<uint8_t>(hp, b);
+        const size_t pack_used = (size_t) (hp - pack.data());
+        int64_t urows = ix->upper_rows;
+        for (int64_t i = 0; i < b; i++) {
+            h_ucand[i] = ucand_row[i];
+            h_final[i] = (int32_t) (cur + i);
+            h_nuoff[i] = -1;
+            h_tid[i] = tid_of(i);
+            h_lev[i] = levels[i];
+            if (levels[i] > 0) {
+                h_nuoff[i] = (int32_t) urows;
+                const int l = std::min<int>(levels[i], EL);
+                for (int r = 0; r < l; r++) { h_durow[ucand_row[i] + r] = (int32_t) (urows + r); h_uown[ucand_row[i] + r] = (int32_t) i; h_ulay[ucand_row[i] + r] = r + 1; }
+                urows += levels[i];
+            }
+        }
+        if (UR == 0) h_durow[0] = -1;
+        if (urows > ix->upper_cap) { set_error("upper layer table full (%lld rows)", (long long) urows); return HB_ENOMEM; }
 
+        hb::DevBuf *W = ix->ws_build;
+        const int64_t E = (int64_t) b * m2 + (int64_t) UR * m;
+        rc = size_workspaces(b, UR1);
+        if (rc) return rc;
+        HB_CK(cudaMemcpyAsync(W[1].p, pack.data(), pack_used, cudaMemcpyHostToDevice, s));
+        char *dp = W[1].as<char>();
+        const int32_t *d_ucand = carve<int32_t>(dp, b);
+        const int32_t *d_final = carve<int32_t>(dp, b);
+        const int32_t *d_nuoff = carve<int32_t>(dp, b);
+        const int32_t *d_durow = carve<int32_t>(dp, UR1);
+        const int32_t *d_uown = carve<int32_t>(dp, UR1);
+        const int32_t *d_ulay = carve<int32_t>(dp, UR1);
+        const int64_t *d_tid = carve<int64_t>(dp, b);
+        const uint8_t *d_lev = carve<uint8_t>(dp, b);
+        // misc words: 0 work counter (fast) | 1 work counter (slow) | 2 slow count | 4 flag | 5 nseg | 6 valid edges
+        unsigned int *misc = ix->ws_misc.as<unsigned int>();
+        HB_CK(cudaMemsetAsync(misc, 0, 32, s));
+        int32_t *d_flag = reinterpret_cast<int32_t *>(misc + 4);
+        int32_t *d_nseg = reinterpret_cast<int32_t *>(misc + 5);
+
+        if (trace) cudaEventRecord(tev[0], s);
+        // ---- candidate search
         BuildSearchParams sp;
         memset(&sp, 0, sizeof sp);
         sp.g = ix->view();
         sp.first = cur; sp.B = (int) b;
-        sp.level = W[1].as<uint8_t>();
-        sp.ucand_row = W[2].as<int32_t>();
+        sp.level = d_lev;
+        sp.ucand_row = d_ucand;
         sp.efc = efc;
         sp.capW = ((efc + 16 + 3) / 4) * 4;
         {
@@ -258,14 +495,14 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         sp.cand0_d = reinterpret_cast<float *>(sp.cand0_id + (size_t) b * efc);
         sp.cand0_cnt = reinterpret_cast<int32_t *>(sp.cand0_d + (size_t) b * efc);
         sp.candu_id = W[4].as<int32_t>();
-        sp.candu_d = reinterpret_cast<float *>(sp.candu_id + (size_t) std::max(UR, 1) * efc);
-        sp.candu_cnt = reinterpret_cast<int32_t *>(sp.candu_d + (size_t) std::max(UR, 1) * efc);
+        sp.candu_d = reinterpret_cast<float *>(sp.candu_id + (size_t) UR1 * efc);
+        sp.candu_cnt = reinterpret_cast<int32_t *>(sp.candu_d + (size_t) UR1 * efc);
         sp.status = W[8].as<int32_t>();
         sp.slow_list = sp.status + b;
         sp.slow_count = reinterpret_cast<int32_t *>(misc + 2);
         sp.totals = ix->d_totals;
         sp.work = misc + 0;
-        const int slow_grid = 16;
+        const int slow_grid = BUILD_SLOW_GRID;
         const int64_t slow_warps = (int64_t) slow_grid * BUILD_WARPS;
         sp.gwords = (int) ((cur + b + 31) / 32 + 1);
         sp.gcap = efc + HB_TIE_LIMIT;
@@ -281,6 +518,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         sps.work = misc + 1; sps.qlist = sp.slow_list; sps.qcount = sp.slow_count;
         HB_CK(HB_PICK(build_search, ix)(sps, ix->num_sms, slow_grid, s, true));
 
+        if (trace) cudaEventRecord(tev[1], s);
         // ---- neighbour selection
         BuildSelectParams lp;
         memset(&lp, 0, sizeof lp);
@@ -291,186 +529,189 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         lp.sel0_d = reinterpret_cast<float *>(lp.sel0_id + (size_t) b * m2);
         lp.sel0_cnt = reinterpret_cast<int32_t *>(lp.sel0_d + (size_t) b * m2);
         lp.selu_id = W[6].as<int32_t>();
-        lp.selu_d = reinterpret_cast<float *>(lp.selu_id + (size_t) std::max(UR, 1) * m);
-        lp.selu_cnt = reinterpret_cast<int32_t *>(lp.selu_d + (size_t) std::max(UR, 1) * m);
-        int32_t *d_dest_urow = lp.selu_cnt + std::max(UR, 1);
+        lp.selu_d = reinterpret_cast<float *>(lp.selu_id + (size_t) UR1 * m);
+        lp.selu_cnt = reinterpret_cast<int32_t *>(lp.selu_d + (size_t) UR1 * m);
         lp.dup = W[7].as<int32_t>();
         lp.totals = ix->d_totals;
         HB_CK(HB_PICK(build_select, ix)(lp, ix->num_sms, s));
+        build_check_kernel<<<(int) ((b + 255) / 256), 256, 0, s>>>(sp.status, lp.dup, (int) b, d_flag);
+        HB_CK(cudaGetLastError());
+        if (trace) cudaEventRecord(tev[2], s);
 
-        // ---- bookkeeping on the host
-        sel0_id.resize((size_t) b * m2); sel0_d.resize((size_t) b * m2); sel0_cnt.resize(b);
-        selu_id.resize((size_t) std::max(UR, 1) * m); selu_d.resize((size_t) std::max(UR, 1) * m); selu_cnt.resize(std::max(UR, 1));
-        dup.resize((size_t) b * DUP_SLOTS); status.resize(b);
-        HB_CK(cudaMemcpyAsync(sel0_id.data(), lp.sel0_id, sizeof(int32_t) * b * m2, cudaMemcpyDeviceToHost, s));
-        HB_CK(cudaMemcpyAsync(sel0_d.data(), lp.sel0_d, sizeof(float) * b * m2, cudaMemcpyDeviceToHost, s));
-        HB_CK(cudaMemcpyAsync(sel0_cnt.data(), lp.sel0_cnt, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, s));
-        if (UR > 0) {
-            HB_CK(cudaMemcpyAsync(selu_id.data(), lp.selu_id, sizeof(int32_t) * UR * m, cudaMemcpyDeviceToHost, s));
-            HB_CK(cudaMemcpyAsync(selu_d.data(), lp.selu_d, sizeof(float) * UR * m, cudaMemcpyDeviceToHost, s));
-            HB_CK(cudaMemcpyAsync(selu_cnt.data(), lp.selu_cnt, sizeof(int32_t) * UR, cudaMemcpyDeviceToHost, s));
-        }
-        HB_CK(cudaMemcpyAsync(dup.data(), lp.dup, sizeof(int32_t) * b * DUP_SLOTS, cudaMemcpyDeviceToHost, s));
-        HB_CK(cudaMemcpyAsync(status.data(), sp.status, sizeof(int32_t) * b, cudaMemcpyDeviceToHost, s));
+        // ---- the tail: AddConnections, reverse links.  Runs once when the no-duplicate assumption
+        // held, a second time with the folded numbering otherwise.
+        char *ep = W[9].as<char>();
+        unsigned long long *key_in = carve<unsigned long long>(ep, E);
+        unsigned long long *key_out = carve<unsigned long long>(ep, E);
+        float *val_in = carve<float>(ep, E);
+        float *val_out = carve<float>(ep, E);
+        int32_t *seg_start = carve<int32_t>(ep, E);
+        int top_bit = 32 + LINK_KEY_SRC_BITS;
+        for (int v = EL; v > 0; v >>= 1) top_bit++;
+        size_t sort_bytes = 0;
+        HB_CK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, key_in, key_out, val_in, val_out, (int) E, 0, top_bit, s));
+        HB_CK(W[10].ensure(sort_bytes + 16));
+
+        auto run_tail = [&](int64_t next, int64_t urows_after) -> int {
+            const int64_t nb_new = next - cur;
+            if (nb_new <= 0) return HB_OK;
+            // clean list rows for the new elements (an element above the old entry level has rows no search filled)
+            HB_CK(cudaMemsetAsync(ix->d_nbr0 + (size_t) cur * m2, 0xff, sizeof(int32_t) * nb_new * m2, s));
+            if (urows_after > ix->upper_rows)
+                HB_CK(cudaMemsetAsync(ix->d_nbru + (size_t) ix->upper_rows * m, 0xff, sizeof(int32_t) * (urows_after - ix->upper_rows) * m, s));
+            CommitParams cp;
+            cp.B = (int) b; cp.UR = UR; cp.m = m;
+            cp.final_id = d_final; cp.new_uoff = d_nuoff; cp.tid = d_tid; cp.dest_urow = d_durow;
+            cp.sel0_id = lp.sel0_id; cp.sel0_d = lp.sel0_d; cp.selu_id = lp.selu_id; cp.selu_d = lp.selu_d;
+            cp.nbr0 = ix->d_nbr0; cp.nbr0d = ix->d_nbr0d; cp.nbru = ix->d_nbru; cp.nbrud = ix->d_nbrud;
+            cp.uoff = ix->d_uoff; cp.tid0 = ix->d_tid0; cp.ntids = ix->d_ntids;
+            cp.pv0 = ix->d_pv0; cp.pvu = ix->d_pvu;
+            cp.flag = d_flag;
+            const int tgrid = (int) ((E + 255) / 256);
+            build_commit_kernel<<<tgrid, 256, 0, s>>>(cp);
+            HB_CK(cudaGetLastError());
+            EdgeGenParams gp;
+            gp.B = (int) b; gp.UR = UR; gp.m = m; gp.first = cur;
+            gp.final_id = d_final; gp.urow_owner = d_uown; gp.urow_layer = d_ulay;
+            gp.sel0_id = lp.sel0_id; gp.sel0_d = lp.sel0_d; gp.sel0_cnt = lp.sel0_cnt;
+            gp.selu_id = lp.selu_id; gp.selu_d = lp.selu_d; gp.selu_cnt = lp.selu_cnt;
+            gp.key = key_in; gp.val = val_in; gp.flag = d_flag;
+            edge_gen_kernel<<<tgrid, 256, 0, s>>>(gp);
+            HB_CK(cudaGetLastError());
+            size_t sb = sort_bytes;
+            HB_CK(cub::DeviceRadixSort::SortPairs(W[10].p, sb, key_in, key_out, val_in, val_out, (int) E, 0, top_bit, s));
+            seg_heads_kernel<<<tgrid, 256, 0, s>>>(key_out, (int) E, seg_start, d_nseg, d_flag);
+            HB_CK(cudaGetLastError());
+            if (trace) cudaEventRecord(tev[3], s);
+            LinkParams kp;
+            memset(&kp, 0, sizeof kp);
+            kp.g = ix->view();
+            kp.g.n = next;
+            kp.first = cur; kp.E = (int) E; kp.nseg = d_nseg; kp.seg_start = seg_start;
+            kp.edge_key = key_out; kp.edge_d = val_out;
+            kp.nbr0 = ix->d_nbr0; kp.nbr0d = ix->d_nbr0d; kp.nbru = ix->d_nbru; kp.nbrud = ix->d_nbrud;
+            kp.totals = ix->d_totals; kp.flag = d_flag;
+            kp.pc0 = ix->d_pc0; kp.pv0 = ix->d_pv0; kp.pcu = ix->d_pcu; kp.pvu = ix->d_pvu;
+            HB_CK(HB_PICK(build_link, ix)(kp, ix->num_sms, ix->opt_link_kernel, s));
+            return HB_OK;
+        };
+
+        rc = run_tail(cur + b, urows);
+        if (rc) return rc;
+        if (trace) cudaEventRecord(tev[4], s);
+        HB_CK(cudaMemcpyAsync(ix->h_flag, d_flag, 12, cudaMemcpyDeviceToHost, s));
+        const double t1 = now();
         HB_CK(cudaStreamSynchronize(s));
-        for (int64_t i = 0; i < b; i++)
-            if (status[i] < 0) {
-                set_error("insert: more than %d candidates tie exactly at the ef_construction boundary", HB_TIE_LIMIT);
-                return HB_ELIMIT;
+        const double t2 = now();
+        t_prep += t1 - t0; t_wait += t2 - t1;
+        if (trace)
+            for (int k = 0; k < 4; k++) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, tev[k], tev[k + 1]) == cudaSuccess) t_dev[k] += ms * 1e-3;
             }
+        const int flag = ix->h_flag[0];
+        n_segs += ix->h_flag[1]; n_edges += ix->h_flag[2];
+        if (flag & 1) {
+            set_error("insert: more than %d candidates tie exactly at the ef_construction boundary", HB_TIE_LIMIT);
+            return HB_ELIMIT;
+        }
 
-        // FindDuplicateInMemory: fold a tuple into the first byte-identical neighbour with room
-        final_id.assign(b, -1);
-        dest_urow.assign(std::max(UR, 1), -1);
-        new_uoff.assign(b, -1);
-        int64_t next = cur;
-        int64_t urows = ix->upper_rows;
-        bool any_dup = false;
+        int64_t next = cur + b;
         std::vector<int32_t> dirty;
+        if (flag & 2) {
+            // FindDuplicateInMemory: fold a tuple into the first byte-identical neighbour with room
+            dup.resize((size_t) b * DUP_SLOTS);
+            HB_CK(cudaMemcpyAsync(dup.data(), lp.dup, sizeof(int32_t) * b * DUP_SLOTS, cudaMemcpyDeviceToHost, s));
+            HB_CK(cudaStreamSynchronize(s));
+            next = cur;
+            urows = ix->upper_rows;
+            for (int r = 0; r < UR1; r++) h_durow[r] = -1;
+            bool any_fold = false;
+            for (int64_t i = 0; i < b; i++) {
+                int32_t into = -1;
+                for (int k = 0; k < DUP_SLOTS; k++) {
+                    const int32_t c = dup[i * DUP_SLOTS + k];
+                    if (c < 0) break;
+                    if (ix->h_ntids[c] < HB_HEAPTIDS) { into = c; break; }
+                }
+                h_nuoff[i] = -1;
+                if (into >= 0) {
+                    ix->h_tids[(size_t) into * HB_HEAPTIDS + ix->h_ntids[into]++] = tid_of(i);
+                    dirty.push_back(into);
+                    h_final[i] = -1;
+                    any_fold = true;
+                    continue;
+                }
+                h_final[i] = (int32_t) next++;
+                if (levels[i] > 0) {
+                    h_nuoff[i] = (int32_t) urows;
+                    const int l = std::min<int>(levels[i], EL);
+                    for (int r = 0; r < l; r++) h_durow[ucand_row[i] + r] = (int32_t) (urows + r);
+                    urows += levels[i];
+                }
+            }
+            if (any_fold && next > cur) {
+                // close the gaps the folded tuples left in [cur, cur + b)
+                HB_CK(ix->ws_build[0].ensure((size_t) b * ix->row_bytes));
+                HB_CK(cudaMemcpyAsync(ix->ws_build[0].p, rows, (size_t) b * ix->row_bytes, cudaMemcpyDeviceToDevice, s));
+                for (int64_t i = 0; i < b; i++)
+                    if (h_final[i] >= 0 && h_final[i] != cur + i)
+                        HB_CK(cudaMemcpyAsync(ix->d_vecs + (size_t) h_final[i] * ix->row_bytes,
+                                              ix->ws_build[0].as<char>() + (size_t) i * ix->row_bytes, ix->row_bytes,
+                                              cudaMemcpyDeviceToDevice, s));
+            }
+            HB_CK(cudaMemcpyAsync(W[1].p, pack.data(), pack_used, cudaMemcpyHostToDevice, s));
+            HB_CK(cudaMemsetAsync(d_flag, 0, 12, s));     // flag, nseg, edge count
+            rc = run_tail(next, urows);
+            if (rc) return rc;
+            HB_CK(cudaStreamSynchronize(s));
+        }
+
+        // ---- host mirrors
         for (int64_t i = 0; i < b; i++) {
-            int32_t into = -1;
-            for (int k = 0; k < DUP_SLOTS; k++) {
-                const int32_t c = dup[i * DUP_SLOTS + k];
-                if (c < 0) break;
-                if (ix->h_ntids[c] < HB_HEAPTIDS) { into = c; break; }
-            }
-            if (into >= 0) {
-                ix->h_tids[(size_t) into * HB_HEAPTIDS + ix->h_ntids[into]++] = tid_of(i);
-                dirty.push_back(into);
-                any_dup = true;
-                continue;
-            }
-            final_id[i] = (int32_t) next++;
+            if (h_final[i] < 0) continue;
             ix->h_level.push_back(levels[i]);
             ix->h_ntids.push_back(1);
             ix->h_tids.resize(ix->h_tids.size() + HB_HEAPTIDS, 0);
-            ix->h_tids[(size_t) final_id[i] * HB_HEAPTIDS] = tid_of(i);
-            if (levels[i] > 0) {
-                new_uoff[i] = (int32_t) urows;
-                const int l = std::min<int>(levels[i], EL);
-                for (int r = 0; r < l; r++) dest_urow[ucand_row[i] + r] = (int32_t) (urows + r);
-                urows += levels[i];
-            }
-        }
-        if (urows > ix->upper_cap) { set_error("upper layer table full (%lld rows)", (long long) urows); return HB_ENOMEM; }
-        const int64_t nb_new = next - cur;
-
-        if (any_dup && nb_new > 0) {
-            // close the gaps the folded tuples left in [cur, cur + b)
-            HB_CK(ix->ws_build[0].ensure((size_t) b * ix->row_bytes));
-            HB_CK(cudaMemcpyAsync(ix->ws_build[0].p, rows, (size_t) b * ix->row_bytes, cudaMemcpyDeviceToDevice, s));
-            for (int64_t i = 0; i < b; i++)
-                if (final_id[i] >= 0 && final_id[i] != cur + i)
-                    HB_CK(cudaMemcpyAsync(ix->d_vecs + (size_t) final_id[i] * ix->row_bytes,
-                                          ix->ws_build[0].as<char>() + (size_t) i * ix->row_bytes, ix->row_bytes,
-                                          cudaMemcpyDeviceToDevice, s));
-        }
-
-        if (nb_new > 0) {
-            // uoff of the new elements, clean list rows, then AddConnections
-            std::vector<int32_t> uo(nb_new);
-            for (int64_t i = 0; i < b; i++) if (final_id[i] >= 0) uo[final_id[i] - cur] = new_uoff[i];
-            HB_CK(cudaMemcpyAsync(ix->d_uoff + cur, uo.data(), sizeof(int32_t) * nb_new, cudaMemcpyHostToDevice, s));
-            HB_CK(cudaMemsetAsync(ix->d_nbr0 + (size_t) cur * m2, 0xff, sizeof(int32_t) * nb_new * m2, s));
-            if (urows > ix->upper_rows)
-                HB_CK(cudaMemsetAsync(ix->d_nbru + (size_t) ix->upper_rows * m, 0xff, sizeof(int32_t) * (urows - ix->upper_rows) * m, s));
-            int32_t *d_final = W[2].as<int32_t>() + b;
-            HB_CK(cudaMemcpyAsync(d_final, final_id.data(), sizeof(int32_t) * b, cudaMemcpyHostToDevice, s));
-            HB_CK(cudaMemcpyAsync(d_dest_urow, dest_urow.data(), sizeof(int32_t) * std::max(UR, 1), cudaMemcpyHostToDevice, s));
-            BuildCommitParams cp;
-            cp.B = (int) b; cp.UR = UR; cp.m = m;
-            cp.final_id = d_final; cp.dest_urow = d_dest_urow;
-            cp.sel0_id = lp.sel0_id; cp.sel0_d = lp.sel0_d; cp.selu_id = lp.selu_id; cp.selu_d = lp.selu_d;
-            cp.nbr0 = ix->d_nbr0; cp.nbr0d = ix->d_nbr0d; cp.nbru = ix->d_nbru; cp.nbrud = ix->d_nbrud;
-            const int64_t threads = (int64_t) b * m2 + (int64_t) UR * m;
-            build_commit_kernel<<<(int) ((threads + 255) / 256), 256, 0, s>>>(cp);
-            HB_CK(cudaGetLastError());
-
-            // reverse links grouped by (layer, target), sources ascending
-            edges.clear();
-            for (int64_t i = 0; i < b; i++) {
-                if (final_id[i] < 0) continue;
-                for (int j = 0; j < sel0_cnt[i]; j++)
-                    edges.push_back({ 0, sel0_id[i * m2 + j], final_id[i], sel0_d[i * m2 + j] });
-                const int l = std::min<int>(levels[i], EL);
-                for (int lc = 1; lc <= l; lc++) {
-                    const int r = ucand_row[i] + (lc - 1);
-                    for (int j = 0; j < selu_cnt[r]; j++)
-                        edges.push_back({ lc, selu_id[(size_t) r * m + j], final_id[i], selu_d[(size_t) r * m + j] });
-                }
-            }
-            std::sort(edges.begin(), edges.end(), [](const Edge &a, const Edge &c) {
-                return std::tie(a.layer, a.target, a.src) < std::tie(c.layer, c.target, c.src);
-            });
-            seg_off.clear(); seg_target.clear(); seg_layer.clear();
-            edge_src.resize(edges.size()); edge_d.resize(edges.size());
-            for (size_t e = 0; e < edges.size(); e++) {
-                if (e == 0 || edges[e].layer != edges[e - 1].layer || edges[e].target != edges[e - 1].target) {
-                    seg_off.push_back((int32_t) e);
-                    seg_target.push_back(edges[e].target);
-                    seg_layer.push_back(edges[e].layer);
-                }
-                edge_src[e] = edges[e].src; edge_d[e] = edges[e].d;
-            }
-            seg_off.push_back((int32_t) edges.size());
-            const int S = (int) seg_target.size();
-            if (S > 0) {
-                const size_t E = edges.size();
-                HB_CK(W[9].ensure(sizeof(int32_t) * (3 * (size_t) S + 1) + 8 * E));
-                int32_t *d_seg_off = W[9].as<int32_t>();
-                int32_t *d_seg_target = d_seg_off + S + 1;
-                int32_t *d_seg_layer = d_seg_target + S;
-                int32_t *d_edge_src = d_seg_layer + S;
-                float *d_edge_d = reinterpret_cast<float *>(d_edge_src + E);
-                HB_CK(cudaMemcpyAsync(d_seg_off, seg_off.data(), sizeof(int32_t) * (S + 1), cudaMemcpyHostToDevice, s));
-                HB_CK(cudaMemcpyAsync(d_seg_target, seg_target.data(), sizeof(int32_t) * S, cudaMemcpyHostToDevice, s));
-                HB_CK(cudaMemcpyAsync(d_seg_layer, seg_layer.data(), sizeof(int32_t) * S, cudaMemcpyHostToDevice, s));
-                HB_CK(cudaMemcpyAsync(d_edge_src, edge_src.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
-                HB_CK(cudaMemcpyAsync(d_edge_d, edge_d.data(), sizeof(float) * E, cudaMemcpyHostToDevice, s));
-                BuildLinkParams kp;
-                memset(&kp, 0, sizeof kp);
-                // the link kernel reads rows and uoff of old and new elements alike
-                ix->n = next; ix->upper_rows = urows;
-                kp.g = ix->view();
-                kp.S = S; kp.seg_off = d_seg_off; kp.seg_target = d_seg_target; kp.seg_layer = d_seg_layer;
-                kp.edge_src = d_edge_src; kp.edge_d = d_edge_d;
-                kp.nbr0 = ix->d_nbr0; kp.nbr0d = ix->d_nbr0d; kp.nbru = ix->d_nbru; kp.nbrud = ix->d_nbrud;
-                kp.totals = ix->d_totals;
-                HB_CK(HB_PICK(build_link, ix)(kp, ix->num_sms, s));
-            }
+            ix->h_tids[(size_t) h_final[i] * HB_HEAPTIDS] = tid_of(i);
             // entry point: the first element whose level exceeds the current entry level
-            for (int64_t i = 0; i < b; i++)
-                if (final_id[i] >= 0 && levels[i] > ix->entry_level) { ix->entry = final_id[i]; ix->entry_level = levels[i]; }
+            if (levels[i] > ix->entry_level) { ix->entry = h_final[i]; ix->entry_level = levels[i]; }
         }
         ix->n = next; ix->upper_rows = urows;
         ix->seq += b;
-        HB_CK(cudaStreamSynchronize(s));   // host vectors above are reused by the next batch
 
-        // heap TIDs on the device
-        if (nb_new > 0 || !dirty.empty()) {
-            std::vector<int64_t> t0(nb_new);
-            std::vector<uint8_t> nt(nb_new, 1);
-            for (int64_t e = 0; e < nb_new; e++) t0[e] = ix->h_tids[(size_t) (cur + e) * HB_HEAPTIDS];
-            if (nb_new > 0) {
-                HB_CK(cudaMemcpy(ix->d_tid0 + cur, t0.data(), sizeof(int64_t) * nb_new, cudaMemcpyHostToDevice));
-                HB_CK(cudaMemcpy(ix->d_ntids + cur, nt.data(), nb_new, cudaMemcpyHostToDevice));
+        // heap TIDs of elements that absorbed a duplicate
+        if (!dirty.empty()) {
+            if (!ix->d_tidx) {
+                HB_CK(cudaMalloc(&ix->d_tidx, sizeof(int64_t) * ix->cap * (HB_HEAPTIDS - 1)));
+                HB_CK(cudaMemset(ix->d_tidx, 0, sizeof(int64_t) * ix->cap * (HB_HEAPTIDS - 1)));
+                ix->has_dups = true;
             }
-            if (!dirty.empty()) {
-                if (!ix->d_tidx) {
-                    HB_CK(cudaMalloc(&ix->d_tidx, sizeof(int64_t) * ix->cap * (HB_HEAPTIDS - 1)));
-                    HB_CK(cudaMemset(ix->d_tidx, 0, sizeof(int64_t) * ix->cap * (HB_HEAPTIDS - 1)));
-                    ix->has_dups = true;
-                }
-                for (int32_t c : dirty) {
-                    HB_CK(cudaMemcpy(ix->d_tidx + (size_t) c * (HB_HEAPTIDS - 1), &ix->h_tids[(size_t) c * HB_HEAPTIDS + 1],
-                                     sizeof(int64_t) * (HB_HEAPTIDS - 1), cudaMemcpyHostToDevice));
-                    HB_CK(cudaMemcpy(ix->d_ntids + c, &ix->h_ntids[c], 1, cudaMemcpyHostToDevice));
-                }
+            for (int32_t c : dirty) {
+                HB_CK(cudaMemcpy(ix->d_tidx + (size_t) c * (HB_HEAPTIDS - 1), &ix->h_tids[(size_t) c * HB_HEAPTIDS + 1],
+                                 sizeof(int64_t) * (HB_HEAPTIDS - 1), cudaMemcpyHostToDevice));
+                HB_CK(cudaMemcpy(ix->d_ntids + c, &ix->h_ntids[c], 1, cudaMemcpyHostToDevice));
             }
         }
         pos += b;
         indexed += b;
+        t_post += now() - t2;
     }
+    if (trace) {
+        fprintf(stderr, "[hb build] device time: search %.3f s, select %.3f s, commit+edges+sort %.3f s, link %.3f s\n",
+                t_dev[0], t_dev[1], t_dev[2], t_dev[3]);
+        for (auto &e : tev) cudaEventDestroy(e);
+#ifdef HB_LINK_PROFILE
+        unsigned long long t[16];
+        cudaMemcpy(t, ix->d_totals, sizeof t, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[hb build] link pipeline, warp-cycles: consumers total %.3g = wait %.3g + tiles %.3g + finalize %.3g (of which extra edges %.3g; %llu finalizes); producer total %.3g, waiting for a free stage %.3g; finalize parts: sort %.3g masks %.3g select %.3g\n",
+                (double) t[12], (double) t[6], (double) t[7], (double) t[8], (double) t[9], t[13], (double) t[11], (double) t[10],
+                (double) t[14], (double) t[15], (double) t[5]);
+#endif
+    }
+    if (trace)
+        fprintf(stderr, "[hb build] %lld tuples in %lld batches: %.3f s total; host enqueue %.3f s, waiting for the device %.3f s, bookkeeping %.3f s; %lld reverse links in %lld (layer, target) segments\n",
+                (long long) indexed, (long long) n_batches, now() - t_begin, t_prep, t_wait, t_post, (long long) n_edges, (long long) n_segs);
     return indexed;
 }
 

@@ -6,14 +6,15 @@
 //                            elements against the graph as it stood before the batch
 //   build_select_kernel   <- hnswutils.c SelectNeighbors + CheckElementCloser (heuristic with pruned
 //                            back-fill) and hnswbuild.c FindDuplicateInMemory
-//   build_commit_kernel   <- hnswutils.c AddConnections
-//   build_link_kernel     <- hnswutils.c HnswUpdateConnection (reverse links; re-selection when the
-//                            neighbour's list is full), one warp per (target, layer), edges applied in
-//                            source-id order
+//   build_commit_kernel   <- hnswutils.c AddConnections (build.cu)
+//   link_pipe_kernel /    <- hnswutils.c HnswUpdateConnection (reverse links; re-selection when the
+//   link_warp_kernel         neighbour's list is full), one CTA or warp per (target, layer), edges
+//                            applied in source-id order (link_kernel.cuh)
 // A batch is what pgvector's parallel build workers are to each other: elements inserted
 // concurrently do not see one another.
 #pragma once
 #include "scan_kernel.cuh"
+#include "link_kernel.cuh"
 #include <cuda_runtime.h>
 
 namespace hb {
@@ -168,9 +169,11 @@ __device__ __forceinline__ int select_neighbors_warp(const GraphView &g, float *
                 const int j = jb + lane;
                 const int32_t nb = (lane < 8 && j < nr) ? r_id[j] : -1;
                 const unsigned mask = __ballot_sync(FULL, nb >= 0);
-                npair += __popc(mask);
                 const float d = eval_candidates<T, IP, NV, G>(g, q, nb, mask, lane);
-                if (__ballot_sync(FULL, nb >= 0 && d <= ed)) closer = false;
+                // n_pair counts what the sequential loop evaluates: up to the first failure
+                const unsigned fail = __ballot_sync(FULL, nb >= 0 && d <= ed);
+                if (fail) { npair += __ffs(fail); closer = false; }
+                else npair += __popc(mask);
             }
         }
         if (lane == 0) {
@@ -263,50 +266,12 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_select_kernel(const Bu
     if (lane == 0 && npair) atomicAdd(p.totals + 4, npair);
 }
 
-// ---- AddConnections: write the selected lists of the surviving new elements -------------------
-struct BuildCommitParams {
-    int B, UR, m;
-    const int32_t *final_id;      // B: element id, or -1 for a tuple folded into a duplicate
-    const int32_t *dest_urow;     // UR: row in nbru, or -1
-    const int32_t *sel0_id; const float *sel0_d;
-    const int32_t *selu_id; const float *selu_d;
-    int32_t *nbr0; float *nbr0d; int32_t *nbru; float *nbrud;
-};
-
-static __global__ void build_commit_kernel(const BuildCommitParams p)
-{
-    const int lm0 = 2 * p.m;
-    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t n0 = (int64_t) p.B * lm0;
-    if (t < n0) {
-        const int i = (int) (t / lm0), j = (int) (t % lm0);
-        const int32_t f = p.final_id[i];
-        if (f >= 0) { p.nbr0[(size_t) f * lm0 + j] = p.sel0_id[t]; p.nbr0d[(size_t) f * lm0 + j] = p.sel0_d[t]; }
-    } else if (t < n0 + (int64_t) p.UR * p.m) {
-        const int64_t u = t - n0;
-        const int r = (int) (u / p.m), j = (int) (u % p.m);
-        const int32_t dr = p.dest_urow[r];
-        if (dr >= 0) { p.nbru[(size_t) dr * p.m + j] = p.selu_id[u]; p.nbrud[(size_t) dr * p.m + j] = p.selu_d[u]; }
-    }
-}
-
-// ---- HnswUpdateConnection -------------------------------------------------------------------
-struct BuildLinkParams {
-    GraphView g;
-    int S;                         // segments = distinct (target, layer) pairs
-    const int32_t *seg_off;        // S + 1
-    const int32_t *seg_target;     // S
-    const int32_t *seg_layer;      // S
-    const int32_t *edge_src;       // E, ascending source id within a segment
-    const float *edge_d;           // E
-    int32_t *nbr0; float *nbr0d; int32_t *nbru; float *nbrud;
-    unsigned long long *totals;
-};
-
+// ---- HnswUpdateConnection, one warp per segment (see link_kernel.cuh) --------------------------
 template <typename T, bool IP, int NV, int G>
-__global__ void __launch_bounds__(BUILD_WARPS * 32) build_link_kernel(const BuildLinkParams p)
+__global__ void __launch_bounds__(BUILD_WARPS * 32) link_warp_kernel(const LinkParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
+    if (*p.flag) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const GraphView &g = p.g;
     const int lm0 = 2 * g.m, cap = lm0 + 1;
@@ -323,9 +288,12 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_link_kernel(const Buil
     float *r_d = reinterpret_cast<float *>(r_id + lm0);
 
     unsigned long long npair = 0;
-    for (int seg = blockIdx.x * BUILD_WARPS + warp; seg < p.S; seg += gridDim.x * BUILD_WARPS) {
-        const int32_t target = p.seg_target[seg];
-        const int lc = p.seg_layer[seg];
+    const int S = *p.nseg;
+    for (int seg = blockIdx.x * BUILD_WARPS + warp; seg < S; seg += gridDim.x * BUILD_WARPS) {
+        const int e0 = p.seg_start[seg];
+        const unsigned long long key0 = p.edge_key[e0] >> LINK_KEY_SRC_BITS;
+        const int lc = (int) (key0 >> 32);
+        const int32_t target = (int32_t) (key0 & 0xffffffffu);
         const int lm = lc == 0 ? lm0 : g.m;
         int32_t *gl;
         float *gld;
@@ -343,8 +311,10 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_link_kernel(const Buil
             cnt += __popc(__ballot_sync(FULL, v >= 0));
         }
         __syncwarp();
-        for (int e = p.seg_off[seg]; e < p.seg_off[seg + 1]; e++) {
-            const int32_t src = p.edge_src[e];
+        for (int e = e0; e < p.E; e++) {
+            const unsigned long long key = p.edge_key[e];
+            if ((key >> LINK_KEY_SRC_BITS) != key0) break;
+            const int32_t src = (int32_t) (p.first + (int64_t) (key & ((1u << LINK_KEY_SRC_BITS) - 1)));
             const float d = p.edge_d[e];
             if (cnt < lm) {
                 if (lane == 0) { l_id[cnt] = src; l_d[cnt] = d; }
@@ -381,6 +351,129 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_link_kernel(const Buil
         }
         for (int j = lane; j < lm; j += 32) {
             if (j < cnt) { gl[j] = l_id[j]; gld[j] = l_d[j]; }
+        }
+    }
+    if (lane == 0 && npair) atomicAdd(p.totals + 4, npair);
+}
+
+// ---- HnswUpdateConnection with memoised pair distances ------------------------------------------
+// A shrink replaces at most one member of the list, so the distances AMONG the members survive it:
+// each list keeps the strict lower triangle of its members' distance matrix (by slot) in HBM.  A
+// shrink then costs lm new pairs (new element <-> members: one staged row, one gather of lm rows)
+// plus the selection replayed on the matrix, instead of the ~125 pairs CheckElementCloser asks for.
+// The first shrink of a list fills its matrix (lm(lm-1)/2 pairs).  Results and n_pair are those of
+// the sequential algorithm (the distances are the same numbers, computed once).  One warp per
+// segment; per warp in shared memory: staged row, matrix, list, sort scratch.
+template <typename T> __host__ __device__ inline size_t memo_warp_smem(int nvec, int lm0)
+{
+    const int cap = lm0 + 1;
+    size_t b = (size_t) nvec * Vec<T>::VEC * 4 + (size_t) cap * cap * 4 + (size_t) cap * 8 + ((cap + 7) & ~7);
+    return (b + 15) & ~(size_t) 15;
+}
+
+template <typename T, bool IP, int NV, int G>
+__global__ void __launch_bounds__(BUILD_WARPS * 32) link_memo_kernel(const LinkParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    if (*p.flag) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const GraphView &g = p.g;
+    const int lm0 = 2 * g.m, cap = lm0 + 1, ld = cap;
+    unsigned char *base = smem + memo_warp_smem<T>(g.nvec, lm0) * warp;
+    float *q = reinterpret_cast<float *>(base);
+    float *D = reinterpret_cast<float *>(base + (size_t) g.nvec * Vec<T>::VEC * 4);
+    int32_t *l_id = reinterpret_cast<int32_t *>(D + cap * cap);
+    float *l_d = reinterpret_cast<float *>(l_id + cap);
+    uint8_t *ord = reinterpret_cast<uint8_t *>(l_d + cap);
+
+    unsigned long long npair = 0;
+    const int S = *p.nseg;
+    for (int seg = blockIdx.x * BUILD_WARPS + warp; seg < S; seg += gridDim.x * BUILD_WARPS) {
+        const int e0 = p.seg_start[seg];
+        const unsigned long long key0 = p.edge_key[e0] >> LINK_KEY_SRC_BITS;
+        const int lc = (int) (key0 >> 32);
+        const int32_t target = (int32_t) (key0 & 0xffffffffu);
+        const int lm = lc == 0 ? lm0 : g.m;
+        const int tri = lm * (lm - 1) / 2;
+        int32_t *gl;
+        float *gld, *pc;
+        uint8_t *pv;
+        if (lc == 0) {
+            gl = p.nbr0 + (size_t) target * lm0; gld = p.nbr0d + (size_t) target * lm0;
+            pc = p.pc0 + (size_t) target * tri; pv = p.pv0 + target;
+        } else {
+            const size_t row = (size_t) g.uoff[target] + (lc - 1);
+            gl = p.nbru + row * g.m; gld = p.nbrud + row * g.m;
+            pc = p.pcu + row * tri; pv = p.pvu + row;
+        }
+        __syncwarp();
+        int cnt = 0;
+        for (int jb = 0; jb < lm; jb += 32) {
+            const int j = jb + lane;
+            int32_t v = -1;
+            if (j < lm) { v = gl[j]; l_id[j] = v; l_d[j] = gld[j]; }
+            cnt += __popc(__ballot_sync(FULL, v >= 0));
+        }
+        __syncwarp();
+        bool have_matrix = false;
+        for (int e = e0; e < p.E; e++) {
+            const unsigned long long key = p.edge_key[e];
+            if ((key >> LINK_KEY_SRC_BITS) != key0) break;
+            const int32_t src = (int32_t) (p.first + (int64_t) (key & ((1u << LINK_KEY_SRC_BITS) - 1)));
+            const float d = p.edge_d[e];
+            if (lane == 0) { l_id[cnt] = src; l_d[cnt] = d; }      // slot cnt <= lm
+            __syncwarp();
+            if (cnt < lm) { cnt++; continue; }
+            if (!have_matrix) {
+                if (*pv) {
+                    for (int a = 1; a < lm; a++) {
+                        const float *rowp = pc + a * (a - 1) / 2;
+                        for (int b = lane; b < a; b += 32) { const float v = rowp[b]; D[a * ld + b] = v; D[b * ld + a] = v; }
+                    }
+                } else {
+                    // first shrink of this list: distances among its members
+                    for (int a = 1; a < lm; a++) {
+                        __syncwarp();
+                        stage_row<T>(g.vecs + (size_t) l_id[a] * g.row_bytes, g.nvec, q, lane);
+                        __syncwarp();
+                        for (int jb = 0; jb < a; jb += 32) {
+                            const int j = jb + lane;
+                            const int32_t nb = j < a ? l_id[j] : -1;
+                            const float v = eval_candidates<T, IP, NV, G>(g, q, nb, __ballot_sync(FULL, nb >= 0), lane);
+                            if (j < a) { D[a * ld + j] = v; D[j * ld + a] = v; }
+                        }
+                    }
+                }
+                have_matrix = true;
+            }
+            // the new element against the members
+            __syncwarp();
+            stage_row<T>(g.vecs + (size_t) src * g.row_bytes, g.nvec, q, lane);
+            __syncwarp();
+            for (int jb = 0; jb < lm; jb += 32) {
+                const int j = jb + lane;
+                const int32_t nb = j < lm ? l_id[j] : -1;
+                const float v = eval_candidates<T, IP, NV, G>(g, q, nb, __ballot_sync(FULL, nb >= 0), lane);
+                if (j < lm) { D[lm * ld + j] = v; D[j * ld + lm] = v; }
+            }
+            __syncwarp();
+            const int ps = link_select_slot(D, ld, l_id, l_d, ord, lm, lane, npair);
+            if (ps != lm) {
+                // the new element takes the pruned member's slot: list entry, matrix row and column
+                for (int b = lane; b < lm; b += 32)
+                    if (b != ps) { const float v = D[lm * ld + b]; D[ps * ld + b] = v; D[b * ld + ps] = v; }
+                if (lane == 0) { l_id[ps] = src; l_d[ps] = d; }
+            }
+            __syncwarp();
+        }
+        for (int j = lane; j < lm; j += 32)
+            if (j < cnt) { gl[j] = l_id[j]; gld[j] = l_d[j]; }
+        if (have_matrix) {
+            for (int a = 1; a < lm; a++) {
+                float *rowp = pc + a * (a - 1) / 2;
+                for (int b = lane; b < a; b += 32) rowp[b] = D[a * ld + b];
+            }
+            if (lane == 0) *pv = 1;
         }
     }
     if (lane == 0 && npair) atomicAdd(p.totals + 4, npair);
@@ -482,19 +575,58 @@ cudaError_t launch_build_select_t(const BuildSelectParams &p, int num_sms, cudaS
     return err;
 }
 
+// which: 0 = automatic: the memoising kernel when the pair cache is allocated and m <= 31, else the
+// pipelined kernel when two stages of lm+1 rows fit shared memory, else the warp kernel;
+// 1 = warp kernel, 2 = pipelined kernel, 3 = memoising kernel (error when the choice cannot run)
 template <typename T, bool IP>
-cudaError_t launch_build_link_t(const BuildLinkParams &p, int num_sms, cudaStream_t stream)
+cudaError_t launch_build_link_t(const LinkParams &p, int num_sms, int which, cudaStream_t stream)
 {
     cudaError_t err = cudaSuccess;
-    if (p.S <= 0) return err;
+    if (p.E <= 0) return err;
+    const int lm0 = 2 * p.g.m;
+    const size_t stage = link_stage_bytes(p.g.row_bytes, lm0), shared = link_shared_bytes(lm0);
+    const size_t limit = 227 * 1024;
+    int nstages = shared < limit ? (int) ((limit - shared) / stage) : 0;
+    if (nstages > LINK_MAX_STAGES) nstages = LINK_MAX_STAGES;
+    const bool can = lm0 <= LINK_MAX_LM && nstages >= 1 && link_num_tiles(LinkTile<T>::TA, lm0) <= LINK_MAX_TILES;
+    if (which == 2 && !can) return cudaErrorInvalidConfiguration;
+    const bool can_memo = p.pc0 != nullptr && lm0 <= LINK_MAX_LM;
+    if (which == 3 && !can_memo) return cudaErrorInvalidConfiguration;
+    if (which == 3 || (which == 0 && can_memo)) {
 #define HB_CALL(NVV, GG)                                                                           \
     {                                                                                              \
-        auto kern = build_link_kernel<T, IP, NVV, (GG > 4 ? 4 : GG)>;                              \
+        auto kern = link_memo_kernel<T, IP, NVV, (GG > 4 ? 4 : GG)>;                               \
+        const size_t smem = memo_warp_smem<T>(p.g.nvec, lm0) * BUILD_WARPS;                        \
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+        if (err == cudaSuccess) {                                                                  \
+            int grid = (p.E + BUILD_WARPS - 1) / BUILD_WARPS;                                      \
+            if (grid > num_sms * 8) grid = num_sms * 8;                                            \
+            kern<<<grid, BUILD_WARPS * 32, smem, stream>>>(p);                                     \
+            err = cudaGetLastError();                                                              \
+        }                                                                                          \
+    }
+        HB_NV_DISPATCH(p.g.nvec, HB_CALL)
+#undef HB_CALL
+        return err;
+    }
+    if (which == 2 || (which == 0 && can && nstages >= 2)) {
+        auto kern = link_pipe_kernel<T, IP>;
+        const size_t smem = stage * nstages + shared;
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (err != cudaSuccess) return err;
+        int64_t grid = num_sms;
+        if (grid > (p.E + LINK_PREFETCH - 1) / LINK_PREFETCH) grid = (p.E + LINK_PREFETCH - 1) / LINK_PREFETCH;
+        kern<<<(int) grid, LINK_THREADS, smem, stream>>>(p, nstages);
+        return cudaGetLastError();
+    }
+#define HB_CALL(NVV, GG)                                                                           \
+    {                                                                                              \
+        auto kern = link_warp_kernel<T, IP, NVV, (GG > 4 ? 4 : GG)>;                               \
         const int cap = 2 * p.g.m + 1;                                                             \
         const size_t smem = select_warp_smem<T>(p.g.nvec, 3 * cap / 2 + 2, 2 * p.g.m) * BUILD_WARPS; \
         err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
         if (err == cudaSuccess) {                                                                  \
-            int grid = (p.S + BUILD_WARPS - 1) / BUILD_WARPS;                                      \
+            int grid = (p.E + BUILD_WARPS - 1) / BUILD_WARPS;                                      \
             if (grid > num_sms * 8) grid = num_sms * 8;                                            \
             kern<<<grid, BUILD_WARPS * 32, smem, stream>>>(p);                                     \
             err = cudaGetLastError();                                                              \

@@ -79,6 +79,11 @@ struct hb_index {
     int32_t *d_uoff = nullptr;
     int32_t *d_nbru = nullptr;
     float *d_nbrud = nullptr;
+    // pair cache of the link phase (build only): distances among each list's members, strict lower
+    // triangle by slot, + filled flag; absent when it would not fit (opt_pair_cache 0 disables)
+    float *d_pc0 = nullptr, *d_pcu = nullptr;
+    uint8_t *d_pv0 = nullptr, *d_pvu = nullptr;
+    bool pair_cache_tried = false;
     int64_t *d_tid0 = nullptr;     // first heap TID of each element
     uint8_t *d_ntids = nullptr;
     int64_t *d_tidx = nullptr;     // remaining HB_HEAPTIDS-1 TIDs, allocated when duplicates exist
@@ -89,6 +94,8 @@ struct hb_index {
 
     // tuning knobs (0 = automatic)
     int opt_slots = 0, opt_grid = 0, opt_build_batch = 0, opt_per_query = 0, opt_variant = 0, opt_no_slow = 0;
+    int opt_pair_cache = 1;
+    int opt_link_kernel = 0;       // 0 automatic, 1 warp-per-segment, 2 CTA-per-segment (link_kernel.cuh)
 
     // workspaces
     cudaStream_t stream = nullptr;
@@ -99,6 +106,7 @@ struct hb_index {
     std::map<void *, hb::ScanWs *> stream_ws;                       // device API: one workspace per user stream
     hb::ScanWs *last_ws = nullptr;
     hb::DevBuf ws_build[12];
+    int32_t *h_flag = nullptr;                // pinned: per-batch flag word of the build pipeline
     unsigned long long *d_totals = nullptr;   // n_dist, n_hop0, n_hopu, n_slow, n_pair, ...
     hb_counters host_totals = {0, 0, 0, 0, 0};
     bool timing_valid = false;
@@ -140,6 +148,7 @@ int normalize_dev(hb_index *ix, const void *dev_in, int64_t n, void *dev_out, cu
 void bruteforce_release(const hb_index *ix);
 // build.cu
 int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n, const int64_t *heap_tids);
+void release_pair_cache(hb_index *ix);
 int level_for(uint64_t seed, int64_t seq, int m);
 uint64_t splitmix64(uint64_t x);
 }   // namespace hb

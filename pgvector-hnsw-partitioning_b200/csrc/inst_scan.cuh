@@ -27,9 +27,9 @@ cudaError_t HB_CAT(build_select_, HBI_NAME)(const BuildSelectParams &p, int sms,
 {
     return launch_build_select_t<HBI_T, HBI_IP>(p, sms, s);
 }
-cudaError_t HB_CAT(build_link_, HBI_NAME)(const BuildLinkParams &p, int sms, cudaStream_t s)
+cudaError_t HB_CAT(build_link_, HBI_NAME)(const LinkParams &p, int sms, int which, cudaStream_t s)
 {
-    return launch_build_link_t<HBI_T, HBI_IP>(p, sms, s);
+    return launch_build_link_t<HBI_T, HBI_IP>(p, sms, which, s);
 }
 cudaError_t HB_CAT(nbr_dist_, HBI_NAME)(const NbrDistParams &p, int sms, cudaStream_t s)
 {

@@ -17,6 +17,8 @@ xh = (x.half() if half else x).cpu().numpy()
 ix = pkg.HnswIndex(dim, opc, 16, 64, capacity=n, seed=1)
 if batch:
     ix.set_option("build_batch", batch)
+if os.environ.get("LINK"):
+    ix.set_option("link_kernel", int(os.environ["LINK"]))
 t0 = time.time(); ix.build(xh); dt = time.time() - t0
 c = ix.counters(reset=True)
 row = dim * (2 if half else 4)
