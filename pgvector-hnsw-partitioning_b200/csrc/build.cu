@@ -29,7 +29,8 @@ namespace hb {
 #define HB_DECLB(name)                                                                                   \
     cudaError_t build_search_##name(const BuildSearchParams &, int, int, cudaStream_t, bool slow);       \
     cudaError_t build_select_##name(const BuildSelectParams &, int, cudaStream_t);                       \
-    cudaError_t build_link_##name(const LinkParams &, int, int, cudaStream_t);                           \
+    cudaError_t build_link_##name(const LinkParams &, int, int, cudaStream_t);                            \
+    cudaError_t pair_fill_##name(const LinkParams &, int, int, cudaStream_t);                           \
     cudaError_t nbr_dist_##name(const NbrDistParams &, int, cudaStream_t);
 HB_DECLB(f32_l2) HB_DECLB(f32_ip) HB_DECLB(f16_l2) HB_DECLB(f16_ip)
 #undef HB_DECLB
@@ -227,6 +228,28 @@ static __global__ void seg_heads_kernel(const unsigned long long *__restrict__ k
     if (e == 0 || (key[e - 1] >> LINK_KEY_SRC_BITS) != (k >> LINK_KEY_SRC_BITS)) seg_start[atomicAdd(nseg, 1)] = e;
 }
 
+// lists that this batch will shrink and whose pair cache is still unfilled: (layer << 32 | target)
+static __global__ void fill_list_kernel(const unsigned long long *__restrict__ key, const int32_t *__restrict__ seg_start,
+                                        const int32_t *__restrict__ nseg, int m, const int32_t *__restrict__ nbr0,
+                                        const int32_t *__restrict__ uoff, const int32_t *__restrict__ nbru,
+                                        const uint8_t *__restrict__ pv0, const uint8_t *__restrict__ pvu,
+                                        unsigned long long *fill_list, int32_t *nfill, const int32_t *flag)
+{
+    if (*flag) return;
+    const int sgm = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sgm >= *nseg) return;
+    const unsigned long long key0 = key[seg_start[sgm]] >> LINK_KEY_SRC_BITS;
+    const int lc = (int) (key0 >> 32);
+    const int32_t target = (int32_t) (key0 & 0xffffffffu);
+    bool want;
+    if (lc == 0) want = pv0[target] == 0 && nbr0[(size_t) target * 2 * m + 2 * m - 1] >= 0;
+    else {
+        const size_t row = (size_t) uoff[target] + (lc - 1);
+        want = pvu[row] == 0 && nbru[row * m + m - 1] >= 0;
+    }
+    if (want) fill_list[atomicAdd(nfill, 1)] = key0;
+}
+
 // AddConnections plus the per-element words of the new elements (uoff, first heap TID)
 struct CommitParams {
     int B, UR, m;
@@ -309,7 +332,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
     double t_dev[4] = { 0, 0, 0, 0 };   // upload+search | select | commit+edges+sort | link
     if (trace) for (auto &e : tev) HB_CK(cudaEventCreate(&e));
 
-    const int max_batch = std::min(ix->opt_build_batch > 0 ? ix->opt_build_batch : 4096, 1 << LINK_KEY_SRC_BITS);
+    const int max_batch = std::min(ix->opt_build_batch > 0 ? ix->opt_build_batch : 8192, 1 << LINK_KEY_SRC_BITS);
     int64_t indexed = 0;
     size_t pos = 0;
     std::vector<char> stage, pack;
@@ -328,7 +351,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         HB_CK(W[6].ensure((size_t) UR1 * m * 8 + sizeof(int32_t) * UR1));     // selu id | d | cnt
         HB_CK(W[7].ensure(sizeof(int32_t) * b * DUP_SLOTS));
         HB_CK(W[8].ensure(sizeof(int32_t) * b * 2 + 64));                     // status | slow list
-        HB_CK(W[9].ensure((size_t) E * (8 + 8 + 4 + 4 + 4) + 128));           // keys in/out | vals in/out | seg_start
+        HB_CK(W[9].ensure((size_t) E * (8 + 8 + 4 + 4 + 4 + 8) + 256));       // keys in/out | vals in/out | seg_start | fill list
         if (ix->metric == HB_COSINE) HB_CK(ix->ws_build[0].ensure((size_t) b * src_row));
         HB_CK(ix->ws_misc.ensure(256));
         return HB_OK;
@@ -467,7 +490,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         const int32_t *d_ulay = carve<int32_t>(dp, UR1);
         const int64_t *d_tid = carve<int64_t>(dp, b);
         const uint8_t *d_lev = carve<uint8_t>(dp, b);
-        // misc words: 0 work counter (fast) | 1 work counter (slow) | 2 slow count | 4 flag | 5 nseg | 6 valid edges
+        // misc words: 0 work counter (fast) | 1 work counter (slow) | 2 slow count | 4 flag | 5 nseg | 6 valid edges | 7 lists to fill
         unsigned int *misc = ix->ws_misc.as<unsigned int>();
         HB_CK(cudaMemsetAsync(misc, 0, 32, s));
         int32_t *d_flag = reinterpret_cast<int32_t *>(misc + 4);
@@ -546,6 +569,8 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         float *val_in = carve<float>(ep, E);
         float *val_out = carve<float>(ep, E);
         int32_t *seg_start = carve<int32_t>(ep, E);
+        unsigned long long *fill_list = carve<unsigned long long>(ep, E);
+        int32_t *d_nfill = reinterpret_cast<int32_t *>(misc + 7);
         int top_bit = 32 + LINK_KEY_SRC_BITS;
         for (int v = EL; v > 0; v >>= 1) top_bit++;
         size_t sort_bytes = 0;
@@ -592,6 +617,16 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
             kp.nbr0 = ix->d_nbr0; kp.nbr0d = ix->d_nbr0d; kp.nbru = ix->d_nbru; kp.nbrud = ix->d_nbrud;
             kp.totals = ix->d_totals; kp.flag = d_flag;
             kp.pc0 = ix->d_pc0; kp.pv0 = ix->d_pv0; kp.pcu = ix->d_pcu; kp.pvu = ix->d_pvu;
+            if (ix->d_pc0 && (ix->opt_link_kernel == 0 || ix->opt_link_kernel == 3) && ix->opt_pair_fill) {
+                // pair-cache fill pre-pass: triangles of the full, still unfilled lists this batch shrinks
+                fill_list_kernel<<<tgrid, 256, 0, s>>>(key_out, seg_start, d_nseg, m, ix->d_nbr0, ix->d_uoff, ix->d_nbru,
+                                                        ix->d_pv0, ix->d_pvu, fill_list, d_nfill, d_flag);
+                HB_CK(cudaGetLastError());
+                LinkParams fp = kp;
+                fp.fill_list = fill_list; fp.nfill = d_nfill;
+                const cudaError_t fe = HB_PICK(pair_fill, ix)(fp, ix->num_sms, (int) std::min<int64_t>(E, 2 * b + UR), s);
+                if (fe != cudaSuccess && fe != cudaErrorInvalidConfiguration) HB_CK(fe);
+            }
             HB_CK(HB_PICK(build_link, ix)(kp, ix->num_sms, ix->opt_link_kernel, s));
             return HB_OK;
         };
@@ -661,7 +696,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
                                               cudaMemcpyDeviceToDevice, s));
             }
             HB_CK(cudaMemcpyAsync(W[1].p, pack.data(), pack_used, cudaMemcpyHostToDevice, s));
-            HB_CK(cudaMemsetAsync(d_flag, 0, 12, s));     // flag, nseg, edge count
+            HB_CK(cudaMemsetAsync(d_flag, 0, 16, s));     // flag, nseg, edge count, fill count
             rc = run_tail(next, urows);
             if (rc) return rc;
             HB_CK(cudaStreamSynchronize(s));

@@ -367,27 +367,38 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) link_warp_kernel(const LinkP
 template <typename T> __host__ __device__ inline size_t memo_warp_smem(int nvec, int lm0)
 {
     const int cap = lm0 + 1;
-    size_t b = (size_t) nvec * Vec<T>::VEC * 4 + (size_t) cap * cap * 4 + (size_t) cap * 8 + ((cap + 7) & ~7);
+    // two staged rows | matrix | second new element's row of the matrix | list | sort scratch
+    size_t b = (size_t) 2 * nvec * Vec<T>::VEC * 4 + (size_t) cap * cap * 4 + (size_t) cap * 4 + (size_t) cap * 8 + ((cap + 7) & ~7);
     return (b + 15) & ~(size_t) 15;
 }
+// per CTA: triangle index -> (a << 8 | b), so that a list's triangle moves with flat coalesced accesses
+__host__ __device__ inline size_t memo_lut_bytes(int lm0) { return ((size_t) lm0 * (lm0 - 1) / 2 * 2 + 15) & ~(size_t) 15; }
 
 template <typename T, bool IP, int NV, int G>
-__global__ void __launch_bounds__(BUILD_WARPS * 32) link_memo_kernel(const LinkParams p)
+__global__ void __launch_bounds__(BUILD_WARPS * 32, 5) link_memo_kernel(const LinkParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     if (*p.flag) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const GraphView &g = p.g;
     const int lm0 = 2 * g.m, cap = lm0 + 1, ld = cap;
-    unsigned char *base = smem + memo_warp_smem<T>(g.nvec, lm0) * warp;
-    float *q = reinterpret_cast<float *>(base);
-    float *D = reinterpret_cast<float *>(base + (size_t) g.nvec * Vec<T>::VEC * 4);
-    int32_t *l_id = reinterpret_cast<int32_t *>(D + cap * cap);
+    const int qfloats = g.nvec * Vec<T>::VEC;
+    uint16_t *lut = reinterpret_cast<uint16_t *>(smem);
+    unsigned char *base = smem + memo_lut_bytes(lm0) + memo_warp_smem<T>(g.nvec, lm0) * warp;
+    float *q0 = reinterpret_cast<float *>(base);
+    float *q1 = q0 + qfloats;
+    float *D = q1 + qfloats;
+    float *D2 = D + cap * cap;                       // second new element <-> members
+    int32_t *l_id = reinterpret_cast<int32_t *>(D2 + cap);
     float *l_d = reinterpret_cast<float *>(l_id + cap);
     uint8_t *ord = reinterpret_cast<uint8_t *>(l_d + cap);
+    for (int a = 1 + (int) threadIdx.x; a < lm0; a += BUILD_WARPS * 32)
+        for (int b = 0; b < a; b++) lut[a * (a - 1) / 2 + b] = (uint16_t) (a << 8 | b);
+    __syncthreads();
 
     unsigned long long npair = 0;
     const int S = *p.nseg;
+    const unsigned src_mask = (1u << LINK_KEY_SRC_BITS) - 1;
     for (int seg = blockIdx.x * BUILD_WARPS + warp; seg < S; seg += gridDim.x * BUILD_WARPS) {
         const int e0 = p.seg_start[seg];
         const unsigned long long key0 = p.edge_key[e0] >> LINK_KEY_SRC_BITS;
@@ -407,6 +418,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) link_memo_kernel(const LinkP
             pc = p.pcu + row * tri; pv = p.pvu + row;
         }
         __syncwarp();
+        const bool filled = *pv != 0;
         int cnt = 0;
         for (int jb = 0; jb < lm; jb += 32) {
             const int j = jb + lane;
@@ -415,65 +427,113 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) link_memo_kernel(const LinkP
             cnt += __popc(__ballot_sync(FULL, v >= 0));
         }
         __syncwarp();
-        bool have_matrix = false;
-        for (int e = e0; e < p.E; e++) {
-            const unsigned long long key = p.edge_key[e];
-            if ((key >> LINK_KEY_SRC_BITS) != key0) break;
-            const int32_t src = (int32_t) (p.first + (int64_t) (key & ((1u << LINK_KEY_SRC_BITS) - 1)));
-            const float d = p.edge_d[e];
-            if (lane == 0) { l_id[cnt] = src; l_d[cnt] = d; }      // slot cnt <= lm
+        // the segment's edges: lanes read up to 32 of them at once (a longer segment reads again)
+        int e = e0;
+        bool have_matrix = false, more = true;
+        while (more) {
+            const int ee = e + lane;
+            unsigned long long key = LINK_KEY_INVALID;
+            float dk = 0.f;
+            if (ee < p.E) { key = p.edge_key[ee]; dk = p.edge_d[ee]; }
+            const unsigned in_seg = __ballot_sync(FULL, (key >> LINK_KEY_SRC_BITS) == key0);
+            const int navail = in_seg == FULL ? 32 : __ffs(~in_seg) - 1;     // leading run
+            more = navail == 32;
+            int k = 0;
+            // appends while the list has room
+            while (k < navail && cnt < lm) {
+                const int32_t src = (int32_t) (p.first + (int64_t) ((unsigned) __shfl_sync(FULL, key, k) & src_mask));
+                const float d = __shfl_sync(FULL, dk, k);
+                if (lane == 0) { l_id[cnt] = src; l_d[cnt] = d; }
+                cnt++; k++;
+            }
             __syncwarp();
-            if (cnt < lm) { cnt++; continue; }
-            if (!have_matrix) {
-                if (*pv) {
-                    for (int a = 1; a < lm; a++) {
-                        const float *rowp = pc + a * (a - 1) / 2;
-                        for (int b = lane; b < a; b += 32) { const float v = rowp[b]; D[a * ld + b] = v; D[b * ld + a] = v; }
-                    }
-                } else {
-                    // first shrink of this list: distances among its members
-                    for (int a = 1; a < lm; a++) {
-                        __syncwarp();
-                        stage_row<T>(g.vecs + (size_t) l_id[a] * g.row_bytes, g.nvec, q, lane);
-                        __syncwarp();
-                        for (int jb = 0; jb < a; jb += 32) {
-                            const int j = jb + lane;
-                            const int32_t nb = j < a ? l_id[j] : -1;
-                            const float v = eval_candidates<T, IP, NV, G>(g, q, nb, __ballot_sync(FULL, nb >= 0), lane);
-                            if (j < a) { D[a * ld + j] = v; D[j * ld + a] = v; }
+            // shrinks, two new elements per pass over the members' rows
+            while (k < navail) {
+                const int two = k + 1 < navail ? 1 : 0;
+                const int32_t srcA = (int32_t) (p.first + (int64_t) ((unsigned) __shfl_sync(FULL, key, k) & src_mask));
+                const int32_t srcB = (int32_t) (p.first + (int64_t) ((unsigned) __shfl_sync(FULL, key, k + two) & src_mask));
+                const float dA = __shfl_sync(FULL, dk, k), dB = __shfl_sync(FULL, dk, k + two);
+                if (!have_matrix) {
+                    if (filled) {
+#pragma unroll 16
+                        for (int idx = lane; idx < tri; idx += 32) {
+                            const float v = __ldcs(pc + idx);
+                            const int ab = lut[idx], a = ab >> 8, b = ab & 0xff;
+                            D[a * ld + b] = v; D[b * ld + a] = v;
+                        }
+                    } else {
+                        // first shrink of this list: distances among its members
+                        for (int a = 1; a < lm; a++) {
+                            __syncwarp();
+                            stage_row_nv<T, NV>(g.vecs + (size_t) l_id[a] * g.row_bytes, g.nvec, q0, lane);
+                            __syncwarp();
+                            for (int jb = 0; jb < a; jb += 32) {
+                                const int j = jb + lane;
+                                const int32_t nb = j < a ? l_id[j] : -1;
+                                const float v = eval_candidates<T, IP, NV, G>(g, q0, nb, __ballot_sync(FULL, nb >= 0), lane);
+                                if (j < a) { D[a * ld + j] = v; D[j * ld + a] = v; }
+                            }
                         }
                     }
+                    have_matrix = true;
                 }
-                have_matrix = true;
+                // the new elements against the members: every member row is fetched once
+                __syncwarp();
+                stage_row_nv<T, NV>(g.vecs + (size_t) srcA * g.row_bytes, g.nvec, q0, lane);
+                if (two) stage_row_nv<T, NV>(g.vecs + (size_t) srcB * g.row_bytes, g.nvec, q1, lane);
+                __syncwarp();
+                for (int jb = 0; jb < lm; jb += 32) {
+                    const int j = jb + lane;
+                    const int32_t nb = j < lm ? l_id[j] : -1;
+                    const unsigned msk = __ballot_sync(FULL, nb >= 0);
+                    if (two) {
+                        float vA, vB;
+                        eval_candidates2<T, IP, NV, (G > 2 ? 2 : G)>(g, q0, q1, nb, msk, lane, vA, vB);
+                        if (j < lm) { D[lm * ld + j] = vA; D[j * ld + lm] = vA; D2[j] = vB; }
+                    } else {
+                        const float vA = eval_candidates<T, IP, NV, G>(g, q0, nb, msk, lane);
+                        if (j < lm) { D[lm * ld + j] = vA; D[j * ld + lm] = vA; }
+                    }
+                }
+                float dAB = 0.f;
+                if (two) dAB = staged_pair_distance<T, IP>(q0, q1, g.nvec, lane);
+                if (lane == 0) { l_id[lm] = srcA; l_d[lm] = dA; }
+                __syncwarp();
+                const int psA = link_select_slot(D, ld, l_id, l_d, ord, lm, lane, npair);
+                if (psA != lm) {
+                    // the new element takes the pruned member's slot: list entry, matrix row and column
+                    for (int b = lane; b < lm; b += 32)
+                        if (b != psA) { const float v = D[lm * ld + b]; D[psA * ld + b] = v; D[b * ld + psA] = v; }
+                    if (lane == 0) { l_id[psA] = srcA; l_d[psA] = dA; }
+                }
+                __syncwarp();
+                if (two) {
+                    for (int b = lane; b < lm; b += 32) {
+                        const float v = (b == psA) ? dAB : D2[b];
+                        D[lm * ld + b] = v; D[b * ld + lm] = v;
+                    }
+                    if (lane == 0) { l_id[lm] = srcB; l_d[lm] = dB; }
+                    __syncwarp();
+                    const int psB = link_select_slot(D, ld, l_id, l_d, ord, lm, lane, npair);
+                    if (psB != lm) {
+                        for (int b = lane; b < lm; b += 32)
+                            if (b != psB) { const float v = D[lm * ld + b]; D[psB * ld + b] = v; D[b * ld + psB] = v; }
+                        if (lane == 0) { l_id[psB] = srcB; l_d[psB] = dB; }
+                    }
+                    __syncwarp();
+                }
+                k += 1 + two;
             }
-            // the new element against the members
-            __syncwarp();
-            stage_row<T>(g.vecs + (size_t) src * g.row_bytes, g.nvec, q, lane);
-            __syncwarp();
-            for (int jb = 0; jb < lm; jb += 32) {
-                const int j = jb + lane;
-                const int32_t nb = j < lm ? l_id[j] : -1;
-                const float v = eval_candidates<T, IP, NV, G>(g, q, nb, __ballot_sync(FULL, nb >= 0), lane);
-                if (j < lm) { D[lm * ld + j] = v; D[j * ld + lm] = v; }
-            }
-            __syncwarp();
-            const int ps = link_select_slot(D, ld, l_id, l_d, ord, lm, lane, npair);
-            if (ps != lm) {
-                // the new element takes the pruned member's slot: list entry, matrix row and column
-                for (int b = lane; b < lm; b += 32)
-                    if (b != ps) { const float v = D[lm * ld + b]; D[ps * ld + b] = v; D[b * ld + ps] = v; }
-                if (lane == 0) { l_id[ps] = src; l_d[ps] = d; }
-            }
-            __syncwarp();
+            e += navail;
         }
         for (int j = lane; j < lm; j += 32)
             if (j < cnt) { gl[j] = l_id[j]; gld[j] = l_d[j]; }
         if (have_matrix) {
-            for (int a = 1; a < lm; a++) {
-                float *rowp = pc + a * (a - 1) / 2;
-                for (int b = lane; b < a; b += 32) rowp[b] = D[a * ld + b];
+            for (int idx = lane; idx < tri; idx += 32) {
+                const int ab = lut[idx];
+                __stcs(pc + idx, D[(ab >> 8) * ld + (ab & 0xff)]);
             }
-            if (lane == 0) *pv = 1;
+            if (lane == 0 && !filled) *pv = 1;
         }
     }
     if (lane == 0 && npair) atomicAdd(p.totals + 4, npair);
@@ -596,7 +656,7 @@ cudaError_t launch_build_link_t(const LinkParams &p, int num_sms, int which, cud
 #define HB_CALL(NVV, GG)                                                                           \
     {                                                                                              \
         auto kern = link_memo_kernel<T, IP, NVV, (GG > 4 ? 4 : GG)>;                               \
-        const size_t smem = memo_warp_smem<T>(p.g.nvec, lm0) * BUILD_WARPS;                        \
+        const size_t smem = memo_lut_bytes(lm0) + memo_warp_smem<T>(p.g.nvec, lm0) * BUILD_WARPS;  \
         err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
         if (err == cudaSuccess) {                                                                  \
             int grid = (p.E + BUILD_WARPS - 1) / BUILD_WARPS;                                      \
@@ -635,6 +695,30 @@ cudaError_t launch_build_link_t(const LinkParams &p, int num_sms, int which, cud
     HB_NV_DISPATCH(p.g.nvec, HB_CALL)
 #undef HB_CALL
     return err;
+}
+
+// pair-cache fill pre-pass: link_pipe_kernel in fill mode over p.fill_list.  Returns
+// cudaErrorInvalidConfiguration when the pipelined kernel cannot run for this shape (the memoising
+// kernel then fills in place).
+template <typename T, bool IP>
+cudaError_t launch_pair_fill_t(const LinkParams &p, int num_sms, int max_items, cudaStream_t stream)
+{
+    const int lm0 = 2 * p.g.m;
+    const size_t stage = link_stage_bytes(p.g.row_bytes, lm0), shared = link_shared_bytes(lm0);
+    const size_t limit = 227 * 1024;
+    int nstages = shared < limit ? (int) ((limit - shared) / stage) : 0;
+    if (nstages > LINK_MAX_STAGES) nstages = LINK_MAX_STAGES;
+    if (!(lm0 <= LINK_MAX_LM && nstages >= 1 && link_num_tiles(LinkTile<T>::TA, lm0) <= LINK_MAX_TILES) || !p.fill_list)
+        return cudaErrorInvalidConfiguration;
+    auto kern = link_pipe_kernel<T, IP>;
+    const size_t smem = stage * nstages + shared;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (err != cudaSuccess) return err;
+    int64_t grid = num_sms;
+    if (grid > (max_items + LINK_PREFETCH - 1) / LINK_PREFETCH) grid = (max_items + LINK_PREFETCH - 1) / LINK_PREFETCH;
+    if (grid < 1) grid = 1;
+    kern<<<(int) grid, LINK_THREADS, smem, stream>>>(p, nstages);
+    return cudaGetLastError();
 }
 
 template <typename T, bool IP>

@@ -184,6 +184,104 @@ __device__ __forceinline__ float group_distance(const char *__restrict__ vecs, u
     return IP ? -s : s;   // lane (c * 32/G) .. hold candidate c
 }
 
+// Two queries at once: each candidate row is fetched once and accumulated against both staged
+// queries (same additions per (query, row) pair as group_distance).  Lane c*(32/G).. holds candidate
+// c's distance to q0 in out0 and to q1 in out1.
+template <typename T, bool IP, int NV, int G>
+__device__ __forceinline__ void group_distance2(const char *__restrict__ vecs, uint32_t row_bytes, int nvec,
+                                                const float *q0, const float *q1, const int32_t (&ids)[G], int lane,
+                                                float &out0, float &out1)
+{
+    constexpr int VEC = Vec<T>::VEC;
+    constexpr bool HALF = sizeof(T) == 2;
+    float acc0[G][VEC], acc1[G][VEC];
+#pragma unroll
+    for (int c = 0; c < G; c++)
+#pragma unroll
+        for (int k = 0; k < VEC; k++) { acc0[c][k] = 0.0f; acc1[c][k] = 0.0f; }
+    const char *rp[G];
+#pragma unroll
+    for (int c = 0; c < G; c++) rp[c] = vecs + (uint64_t) (uint32_t) ids[c] * row_bytes + 16 * lane;
+    const int plane = 4 * nvec;
+    if constexpr (NV > 0) {
+        uint4 raw[G][NV];
+#pragma unroll
+        for (int c = 0; c < G; c++)
+#pragma unroll
+            for (int j = 0; j < NV; j++) raw[c][j] = ldg_stream(rp[c] + 512 * j);
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            const int ch = lane + 32 * j;
+            const float4 a0 = *reinterpret_cast<const float4 *>(q0 + 4 * ch);
+            const float4 a1 = *reinterpret_cast<const float4 *>(q1 + 4 * ch);
+            float4 b0 = a0, b1 = a1;
+            if constexpr (HALF) {
+                b0 = *reinterpret_cast<const float4 *>(q0 + plane + 4 * ch);
+                b1 = *reinterpret_cast<const float4 *>(q1 + plane + 4 * ch);
+            }
+#pragma unroll
+            for (int c = 0; c < G; c++) {
+                accum_chunk<T, IP>(acc0[c], raw[c][j], a0, b0);
+                accum_chunk<T, IP>(acc1[c], raw[c][j], a1, b1);
+            }
+        }
+    } else {
+        for (int ch = lane; ch < nvec; ch += 32) {
+            uint4 raw[G];
+#pragma unroll
+            for (int c = 0; c < G; c++) raw[c] = ldg_stream(rp[c] + 16 * (ch - lane));
+            const float4 a0 = *reinterpret_cast<const float4 *>(q0 + 4 * ch);
+            const float4 a1 = *reinterpret_cast<const float4 *>(q1 + 4 * ch);
+            float4 b0 = a0, b1 = a1;
+            if constexpr (HALF) {
+                b0 = *reinterpret_cast<const float4 *>(q0 + plane + 4 * ch);
+                b1 = *reinterpret_cast<const float4 *>(q1 + plane + 4 * ch);
+            }
+#pragma unroll
+            for (int c = 0; c < G; c++) {
+                accum_chunk<T, IP>(acc0[c], raw[c], a0, b0);
+                accum_chunk<T, IP>(acc1[c], raw[c], a1, b1);
+            }
+        }
+    }
+    float part0[G], part1[G];
+#pragma unroll
+    for (int c = 0; c < G; c++) { part0[c] = fold_lane<VEC>(acc0[c]); part1[c] = fold_lane<VEC>(acc1[c]); }
+    const float s0 = XReduce<G>::run(part0, lane, 16), s1 = XReduce<G>::run(part1, lane, 16);
+    out0 = IP ? -s0 : s0;
+    out1 = IP ? -s1 : s1;
+}
+
+// distance between two rows staged in shared memory (stage_row layout), canonical order
+template <typename T, bool IP>
+__device__ __forceinline__ float staged_pair_distance(const float *q0, const float *q1, int nvec, int lane)
+{
+    constexpr int VEC = Vec<T>::VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; k++) acc[k] = 0.0f;
+    const int plane = 4 * nvec;
+    for (int ch = lane; ch < nvec; ch += 32) {
+        float a[VEC], b[VEC];
+        const float4 a0 = *reinterpret_cast<const float4 *>(q0 + 4 * ch), b0 = *reinterpret_cast<const float4 *>(q1 + 4 * ch);
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+        if constexpr (VEC == 8) {
+            const float4 a1 = *reinterpret_cast<const float4 *>(q0 + plane + 4 * ch), b1 = *reinterpret_cast<const float4 *>(q1 + plane + 4 * ch);
+            a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            if constexpr (IP) acc[k] = fmaf(a[k], b[k], acc[k]);
+            else { const float t = a[k] - b[k]; acc[k] = fmaf(t, t, acc[k]); }
+        }
+    }
+    float s = fold_lane<VEC>(acc);
+    for (int b = 16; b >= 1; b >>= 1) s = s + __shfl_xor_sync(FULL, s, b);
+    return IP ? -s : s;
+}
+
 // stage a query (global, index dtype, `dim` components) into shared memory as fp32 in the
 // layout accum_chunk expects; pads with zeros up to the chunk boundary.
 template <typename T>
@@ -223,6 +321,37 @@ __device__ __forceinline__ void stage_row(const char *__restrict__ row, int nvec
             *reinterpret_cast<float4 *>(q + 4 * nvec + 4 * ch) = make_float4(h2.x, h2.y, h3.x, h3.y);
         }
     }
+}
+
+// same, with the row's 128-bit loads issued back to back before any store (row of exactly 32*NV chunks)
+template <typename T, int NV>
+__device__ __forceinline__ void stage_row_nv(const char *__restrict__ row, int nvec, float *q, int lane)
+{
+    if constexpr (NV == 0) stage_row<T>(row, nvec, q, lane);
+    else {
+        uint4 raw[NV];
+#pragma unroll
+        for (int j = 0; j < NV; j++) raw[j] = *reinterpret_cast<const uint4 *>(row + 16 * (lane + 32 * j));
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            const int ch = lane + 32 * j;
+            if constexpr (sizeof(T) == 4) *reinterpret_cast<uint4 *>(q + 4 * ch) = raw[j];
+            else {
+                const float2 h0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[j].x));
+                const float2 h1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[j].y));
+                const float2 h2 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[j].z));
+                const float2 h3 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[j].w));
+                *reinterpret_cast<float4 *>(q + 4 * ch) = make_float4(h0.x, h0.y, h1.x, h1.y);
+                *reinterpret_cast<float4 *>(q + 4 * nvec + 4 * ch) = make_float4(h2.x, h2.y, h3.x, h3.y);
+            }
+        }
+    }
+}
+
+// ask L2 for `bytes` (multiple of 16) at a 16-byte aligned address; returns immediately
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 }   // namespace hb

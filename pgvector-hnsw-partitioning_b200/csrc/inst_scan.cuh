@@ -31,6 +31,10 @@ cudaError_t HB_CAT(build_link_, HBI_NAME)(const LinkParams &p, int sms, int whic
 {
     return launch_build_link_t<HBI_T, HBI_IP>(p, sms, which, s);
 }
+cudaError_t HB_CAT(pair_fill_, HBI_NAME)(const LinkParams &p, int sms, int max_items, cudaStream_t s)
+{
+    return launch_pair_fill_t<HBI_T, HBI_IP>(p, sms, max_items, s);
+}
 cudaError_t HB_CAT(nbr_dist_, HBI_NAME)(const NbrDistParams &p, int sms, cudaStream_t s)
 {
     return launch_nbr_dist_t<HBI_T, HBI_IP>(p, sms, s);

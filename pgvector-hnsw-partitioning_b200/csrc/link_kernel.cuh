@@ -51,6 +51,10 @@ struct LinkParams {
     // triangle, and a byte saying whether it has been filled.  NULL when the cache is not allocated.
     float *pc0; uint8_t *pv0;      // n x lm0(lm0-1)/2, n
     float *pcu; uint8_t *pvu;      // upper_rows x m(m-1)/2, upper_rows
+    // fill mode of link_pipe_kernel: instead of processing segments, fill the pair cache of the
+    // lists named here (key = layer << 32 | target; full lists whose triangle is not filled yet)
+    const unsigned long long *fill_list;
+    const int32_t *nfill;
 };
 
 __device__ __forceinline__ uint32_t link_smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -131,7 +135,7 @@ constexpr int LINK_MAX_TILES = 352;
 constexpr int LINK_TB = 4;
 
 struct LinkStageMeta {
-    int kind;                    // 1 = work, 0 = no more segments
+    int kind;                    // 1 = segment, 2 = fill the pair cache of a list, 0 = no more work
     int lm;                      // list capacity of this layer; candidates = lm + 1
     int e;                       // index of the edge whose new element sits in slot lm
     int ntiles;
@@ -141,6 +145,8 @@ struct LinkStageMeta {
     unsigned long long seg_key;  // key >> LINK_KEY_SRC_BITS of the segment
     int32_t *gl;                 // the list in HBM
     float *gld;
+    float *pc;                   // fill mode (kind 2): where the triangle goes
+    uint8_t *pv;
 };
 
 template <typename T> struct LinkTile { static constexpr int TA = sizeof(T) == 4 ? 4 : 2; };
@@ -301,7 +307,7 @@ __device__ __forceinline__ void link_finalize(const LinkParams &p, const LinkSta
 {
     const GraphView &g = p.g;
     const uint32_t row_bytes = (uint32_t) g.row_bytes;
-    const int lm = st.meta->lm, nc = lm + 1, ld = 2 * g.m + 1;
+    const int lm = st.meta->lm, ld = 2 * g.m + 1;
     const unsigned long long seg_key = st.meta->seg_key;
     int e = st.meta->e;
     long long t_extra = 0;
@@ -391,7 +397,8 @@ __global__ void __launch_bounds__(LINK_THREADS, 1) link_pipe_kernel(const LinkPa
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int S = *p.nseg;
+    const bool fill = p.fill_list != nullptr;
+    const int S = fill ? *p.nfill : *p.nseg;
 
     if (warp == LINK_CW) {
         // ================= producer =================
@@ -399,6 +406,7 @@ __global__ void __launch_bounds__(LINK_THREADS, 1) link_pipe_kernel(const LinkPa
         uint32_t phase = 0;
         long long tp_wait = 0;
         const long long tp0 = LINK_CLK();
+        (void) tp0;
         for (int base = blockIdx.x * LINK_PREFETCH; base < S; base += gridDim.x * LINK_PREFETCH) {
             // lane k reads ahead for segment base + k: key, list location, the list itself
             const int seg = base + lane;
@@ -406,16 +414,24 @@ __global__ void __launch_bounds__(LINK_THREADS, 1) link_pipe_kernel(const LinkPa
             unsigned long long key0 = 0ull;
             int32_t *gl = nullptr;
             float *gld = nullptr;
+            float *pc = nullptr;
+            uint8_t *pv = nullptr;
             if (seg < S) {
-                e0 = p.seg_start[seg];
-                key0 = p.edge_key[e0] >> LINK_KEY_SRC_BITS;
+                if (fill) key0 = p.fill_list[seg];
+                else {
+                    e0 = p.seg_start[seg];
+                    key0 = p.edge_key[e0] >> LINK_KEY_SRC_BITS;
+                }
                 const int lc = (int) (key0 >> 32);
                 const int32_t target = (int32_t) (key0 & 0xffffffffu);
-                if (lc == 0) { gl = p.nbr0 + (size_t) target * lm0; gld = p.nbr0d + (size_t) target * lm0; }
-                else {
+                if (lc == 0) {
+                    gl = p.nbr0 + (size_t) target * lm0; gld = p.nbr0d + (size_t) target * lm0;
+                    if (fill) { pc = p.pc0 + (size_t) target * (lm0 * (lm0 - 1) / 2); pv = p.pv0 + target; }
+                } else {
                     lm = g.m;
                     const size_t row = (size_t) g.uoff[target] + (lc - 1);
                     gl = p.nbru + row * g.m; gld = p.nbrud + row * g.m;
+                    if (fill) { pc = p.pcu + row * (g.m * (g.m - 1) / 2); pv = p.pvu + row; }
                 }
                 int32_t *ci = cache_id + lane * cap;
                 float *cd = cache_d + lane * cap;
@@ -442,6 +458,35 @@ __global__ void __launch_bounds__(LINK_THREADS, 1) link_pipe_kernel(const LinkPa
                 float *cd = cache_d + k * cap;
                 int cnt = 0;
                 for (int jb = 0; jb < lm_k; jb += 32) cnt += __popc(__ballot_sync(FULL, jb + lane < lm_k && ci[jb + lane] >= 0));
+                if (fill) {
+                    // stage the members' rows; the consumers compute their triangle
+                    float *pc_k = reinterpret_cast<float *>(__shfl_sync(FULL, (unsigned long long) pc, k));
+                    uint8_t *pv_k = reinterpret_cast<uint8_t *>(__shfl_sync(FULL, (unsigned long long) pv, k));
+                    if (cnt < lm_k) continue;
+                    const LinkStage st = link_stage_at(smem + stage_bytes * stage, row_bytes, lm0);
+                    link_mbar_wait(st.empty, phase ^ 1u);
+                    if (lane == 0) {
+                        LinkStageMeta *mt = st.meta;
+                        mt->kind = 2; mt->lm = lm_k; mt->e = 0; mt->table = lm_k == lm0 ? 0 : 1;
+                        mt->ntiles = link_num_tiles(TA, lm_k) - (lm_k + TB - 1) / TB; mt->tile_next = 0; mt->tiles_done = 0;
+                        mt->seg_key = key_k; mt->gl = gl_k; mt->gld = gld_k; mt->pc = pc_k; mt->pv = pv_k;
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                                     ::"r"(link_smem_u32(st.full)), "r"((uint32_t) lm_k * row_bytes) : "memory");
+                    }
+                    __syncwarp();
+                    for (int a = lane; a < lm_k; a += 32) {
+                        const char *srcp = g.vecs + (size_t) ci[a] * row_bytes;
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(link_smem_u32(st.rows + (size_t) a * row_bytes)), "l"(srcp), "r"(row_bytes),
+                                       "r"(link_smem_u32(st.full)) : "memory");
+                    }
+                    if (++stage == nstages) { stage = 0; phase ^= 1u; }
+                    continue;
+                }
                 bool handed = false;
                 for (; e < p.E; e++) {
                     const unsigned long long key = p.edge_key[e];
@@ -507,6 +552,7 @@ __global__ void __launch_bounds__(LINK_THREADS, 1) link_pipe_kernel(const LinkPa
     uint32_t phase = 0;
     long long tc_wait = 0, tc_tiles = 0, tc_final = 0, n_final = 0;
     const long long tc0 = LINK_CLK();
+    (void) tc0;
     for (;;) {
         const LinkStage st = link_stage_at(smem + stage_bytes * stage, row_bytes, lm0);
         const long long tw0 = LINK_CLK();
@@ -546,7 +592,12 @@ __global__ void __launch_bounds__(LINK_THREADS, 1) link_pipe_kernel(const LinkPa
         tc_tiles += tw2 - tw1;
         if (last) {
             __threadfence_block();
-            link_finalize<T, IP>(p, st, lane, npair);
+            if (st.meta->kind == 2) {
+                float *pc = st.meta->pc;
+                for (int a = 1; a < lm; a++)
+                    for (int b = lane; b < a; b += 32) __stcs(pc + a * (a - 1) / 2 + b, st.D[a * ld + b]);
+                if (lane == 0) *st.meta->pv = 1;
+            } else link_finalize<T, IP>(p, st, lane, npair);
             __syncwarp();
             tc_final += LINK_CLK() - tw2;
             n_final++;

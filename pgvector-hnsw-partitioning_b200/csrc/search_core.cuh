@@ -252,6 +252,38 @@ __device__ __forceinline__ float eval_candidates(const GraphView &g, const float
     return myd;
 }
 
+// as eval_candidates, against two staged queries: each candidate row is fetched once
+template <typename T, bool IP, int NV, int G>
+__device__ __forceinline__ void eval_candidates2(const GraphView &g, const float *q0, const float *q1, int32_t nb,
+                                                 unsigned mask, int lane, float &d0, float &d1)
+{
+    d0 = d1 = __int_as_float(0x7f800000);
+    unsigned rem = mask;
+#define HB_EVAL_GROUP2(GG)                                                                         \
+    {                                                                                              \
+        int32_t ids[GG];                                                                           \
+        int src[GG];                                                                               \
+        _Pragma("unroll") for (int c = 0; c < GG; c++)                                             \
+        {                                                                                          \
+            src[c] = __ffs(rem) - 1;                                                               \
+            rem &= rem - 1;                                                                        \
+            ids[c] = __shfl_sync(FULL, nb, src[c]);                                                \
+        }                                                                                          \
+        float s0, s1;                                                                              \
+        group_distance2<T, IP, NV, GG>(g.vecs, (uint32_t) g.row_bytes, g.nvec, q0, q1, ids, lane, s0, s1); \
+        _Pragma("unroll") for (int c = 0; c < GG; c++)                                             \
+        {                                                                                          \
+            const float v0 = __shfl_sync(FULL, s0, c * (32 / GG));                                 \
+            const float v1 = __shfl_sync(FULL, s1, c * (32 / GG));                                 \
+            if (lane == src[c]) { d0 = v0; d1 = v1; }                                              \
+        }                                                                                          \
+    }
+    if constexpr (G >= 4) while (__popc(rem) >= 4) HB_EVAL_GROUP2(4)
+    if constexpr (G >= 2) while (__popc(rem) >= 2) HB_EVAL_GROUP2(2)
+    while (rem) HB_EVAL_GROUP2(1)
+#undef HB_EVAL_GROUP2
+}
+
 // HnswSearchLayer.  Precondition: w holds the entry candidates (sorted, unexpanded) and vs holds
 // exactly their ids.  Postcondition: w[0 .. min(L, ef)) = the result, nearest first.
 template <typename T, bool IP, int NV, int G, typename VS>
