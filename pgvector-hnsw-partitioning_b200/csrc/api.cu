@@ -288,6 +288,8 @@ void hb_index_free(hb_index *ix)
     ix->stream_ws.clear();
     for (auto &b : ix->ws_build) b.release();
     if (ix->h_flag) cudaFreeHost(ix->h_flag);
+    if (ix->up_event) cudaEventDestroy(ix->up_event);
+    if (ix->up_stream) cudaStreamDestroy(ix->up_stream);
     if (ix->ev0) cudaEventDestroy(ix->ev0);
     if (ix->ev1) cudaEventDestroy(ix->ev1);
     if (ix->stream) cudaStreamDestroy(ix->stream);

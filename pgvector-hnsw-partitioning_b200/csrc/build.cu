@@ -299,6 +299,7 @@ template <typename V> static inline V *carve(char *&p, size_t count)
 int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const int64_t *heap_tids)
 {
     if (n_in == 0) return 0;
+    const double t_enter = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     HB_CK(cudaSetDevice(ix->device));
     cudaStream_t s = ix->stream;
     const size_t src_row = (size_t) ix->dim * ix->esize;
@@ -315,8 +316,10 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         set_error("index capacity %lld exceeded (%lld + %lld)", (long long) ix->cap, (long long) ix->n, (long long) todo.size());
         return HB_ENOMEM;
     }
+    const double t_todo = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     int rc = ensure_build_arrays(ix, s);
     if (rc) return rc;
+    const double t_arrays = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     ix->h_level.reserve(ix->n + todo.size());
     ix->h_ntids.reserve(ix->n + todo.size());
     ix->h_tids.reserve((ix->n + todo.size()) * HB_HEAPTIDS);
@@ -352,7 +355,6 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         HB_CK(W[7].ensure(sizeof(int32_t) * b * DUP_SLOTS));
         HB_CK(W[8].ensure(sizeof(int32_t) * b * 2 + 64));                     // status | slow list
         HB_CK(W[9].ensure((size_t) E * (8 + 8 + 4 + 4 + 4 + 8) + 256));       // keys in/out | vals in/out | seg_start | fill list
-        if (ix->metric == HB_COSINE) HB_CK(ix->ws_build[0].ensure((size_t) b * src_row));
         HB_CK(ix->ws_misc.ensure(256));
         return HB_OK;
     };
@@ -369,6 +371,52 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         HB_CK(ix->ws_gbits.ensure(sizeof(uint32_t) * slow_warps * ((ix->n + (int64_t) todo.size() + 31) / 32 + 2)));
     }
 
+    // Rows are uploaded (and normalised under the cosine opclass) AHEAD of the batch that indexes
+    // them, on a second stream, while the previous batch's kernels run: todo row t goes to slot
+    // slot_base + t, which holds as long as no tuple folds into a duplicate (the duplicate path
+    // re-bases and re-uploads).  The host blocks in the pageable-memory copy, the device does not.
+    if (!ix->up_stream) HB_CK(cudaStreamCreateWithFlags(&ix->up_stream, cudaStreamNonBlocking));
+    if (!ix->up_event) HB_CK(cudaEventCreateWithFlags(&ix->up_event, cudaEventDisableTiming));
+    cudaStream_t up = ix->up_stream;
+    cudaEvent_t up_ev = ix->up_event;
+    int64_t uploaded = 0;                    // todo rows [0, uploaded) are in HBM or on their way
+    int64_t slot_base = ix->n;
+    const int64_t up_chunk = 16384;
+    // the upload stream must not run ahead of whatever used these slots before this call
+    HB_CK(cudaEventRecord(up_ev, s));
+    HB_CK(cudaStreamWaitEvent(up, up_ev, 0));
+    auto upload_upto = [&](int64_t want) -> int {
+        want = std::min<int64_t>(want, (int64_t) todo.size());
+        while (uploaded < want) {
+            const int64_t c = std::min<int64_t>(std::min<int64_t>(up_chunk, max_batch), (int64_t) todo.size() - uploaded);
+            const char *src = (const char *) host_vecs + todo[uploaded] * src_row;
+            if (todo[uploaded + c - 1] - todo[uploaded] != c - 1) {       // a zero vector was skipped inside the chunk
+                stage.resize((size_t) c * src_row);
+                for (int64_t i = 0; i < c; i++) memcpy(&stage[i * src_row], (const char *) host_vecs + todo[uploaded + i] * src_row, src_row);
+                src = stage.data();
+            }
+            char *rows = ix->d_vecs + (size_t) (slot_base + uploaded) * ix->row_bytes;
+            if (ix->metric == HB_COSINE) {
+                HB_CK(ix->ws_build[0].ensure((size_t) c * src_row));
+                HB_CK(cudaMemcpyAsync(ix->ws_build[0].p, src, (size_t) c * src_row, cudaMemcpyHostToDevice, up));
+                const int wpb = 8, grid = (int) ((c + wpb - 1) / wpb);
+                if (ix->dtype == HB_F32)
+                    normalize_rows_kernel<float><<<grid, wpb * 32, 0, up>>>(ix->ws_build[0].as<float>(), rows, ix->row_bytes, c, ix->dim);
+                else
+                    normalize_rows_kernel<__half><<<grid, wpb * 32, 0, up>>>(ix->ws_build[0].as<__half>(), rows, ix->row_bytes, c, ix->dim);
+                HB_CK(cudaGetLastError());
+            } else if (src_row == ix->row_bytes) {
+                HB_CK(cudaMemcpyAsync(rows, src, src_row * c, cudaMemcpyHostToDevice, up));
+            } else {
+                HB_CK(cudaMemsetAsync(rows, 0, ix->row_bytes * c, up));
+                HB_CK(cudaMemcpy2DAsync(rows, ix->row_bytes, src, src_row, src_row, c, cudaMemcpyHostToDevice, up));
+            }
+            uploaded += c;
+        }
+        HB_CK(cudaEventRecord(up_ev, up));
+        return HB_OK;
+    };
+
     while (pos < todo.size()) {
         const double t0 = now();
         n_batches++;
@@ -384,28 +432,11 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         } else b = 1;
         levels.resize(b);
 
-        // ---- rows into HBM at [cur, cur + b)
-        const char *src = (const char *) host_vecs + todo[pos] * src_row;
-        if (todo[pos + b - 1] - todo[pos] != b - 1) {       // a zero vector was skipped inside the batch
-            stage.resize((size_t) b * src_row);
-            for (int64_t i = 0; i < b; i++) memcpy(&stage[i * src_row], (const char *) host_vecs + todo[pos + i] * src_row, src_row);
-            src = stage.data();
-        }
+        // ---- rows into HBM at [cur, cur + b): normally already there (uploaded ahead, see below)
+        rc = upload_upto((int64_t) pos + b);
+        if (rc) return rc;
+        HB_CK(cudaStreamWaitEvent(s, up_ev, 0));
         char *rows = ix->d_vecs + (size_t) cur * ix->row_bytes;
-        if (ix->metric == HB_COSINE) {
-            HB_CK(cudaMemcpyAsync(ix->ws_build[0].p, src, (size_t) b * src_row, cudaMemcpyHostToDevice, s));
-            const int wpb = 8, grid = (int) ((b + wpb - 1) / wpb);
-            if (ix->dtype == HB_F32)
-                normalize_rows_kernel<float><<<grid, wpb * 32, 0, s>>>(ix->ws_build[0].as<float>(), rows, ix->row_bytes, b, ix->dim);
-            else
-                normalize_rows_kernel<__half><<<grid, wpb * 32, 0, s>>>(ix->ws_build[0].as<__half>(), rows, ix->row_bytes, b, ix->dim);
-            HB_CK(cudaGetLastError());
-        } else if (src_row == ix->row_bytes) {
-            HB_CK(cudaMemcpyAsync(rows, src, src_row * b, cudaMemcpyHostToDevice, s));
-        } else {
-            HB_CK(cudaMemsetAsync(rows, 0, ix->row_bytes * b, s));
-            HB_CK(cudaMemcpy2DAsync(rows, ix->row_bytes, src, src_row, src_row, b, cudaMemcpyHostToDevice, s));
-        }
 
         auto tid_of = [&](int64_t i) { return heap_tids ? heap_tids[todo[pos + i]] : todo[pos + i]; };
 
@@ -635,6 +666,9 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         if (rc) return rc;
         if (trace) cudaEventRecord(tev[4], s);
         HB_CK(cudaMemcpyAsync(ix->h_flag, d_flag, 12, cudaMemcpyDeviceToHost, s));
+        // while the device works on this batch: the rows of the next one (at most ~cur/16 + a chunk ahead)
+        rc = upload_upto((int64_t) pos + b + std::min<int64_t>(max_batch, (cur + b) / 16 + 1));
+        if (rc) return rc;
         const double t1 = now();
         HB_CK(cudaStreamSynchronize(s));
         const double t2 = now();
@@ -687,12 +721,12 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
             }
             if (any_fold && next > cur) {
                 // close the gaps the folded tuples left in [cur, cur + b)
-                HB_CK(ix->ws_build[0].ensure((size_t) b * ix->row_bytes));
-                HB_CK(cudaMemcpyAsync(ix->ws_build[0].p, rows, (size_t) b * ix->row_bytes, cudaMemcpyDeviceToDevice, s));
+                HB_CK(ix->ws_build[11].ensure((size_t) b * ix->row_bytes));
+                HB_CK(cudaMemcpyAsync(ix->ws_build[11].p, rows, (size_t) b * ix->row_bytes, cudaMemcpyDeviceToDevice, s));
                 for (int64_t i = 0; i < b; i++)
                     if (h_final[i] >= 0 && h_final[i] != cur + i)
                         HB_CK(cudaMemcpyAsync(ix->d_vecs + (size_t) h_final[i] * ix->row_bytes,
-                                              ix->ws_build[0].as<char>() + (size_t) i * ix->row_bytes, ix->row_bytes,
+                                              ix->ws_build[11].as<char>() + (size_t) i * ix->row_bytes, ix->row_bytes,
                                               cudaMemcpyDeviceToDevice, s));
             }
             HB_CK(cudaMemcpyAsync(W[1].p, pack.data(), pack_used, cudaMemcpyHostToDevice, s));
@@ -700,6 +734,12 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
             rc = run_tail(next, urows);
             if (rc) return rc;
             HB_CK(cudaStreamSynchronize(s));
+            if (next != cur + b) {
+                // rows uploaded ahead sit at slots computed without the folds: re-base and upload again
+                HB_CK(cudaStreamSynchronize(up));
+                uploaded = (int64_t) pos + b;
+                slot_base = next - uploaded;
+            }
         }
 
         // ---- host mirrors
@@ -733,6 +773,8 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         t_post += now() - t2;
     }
     if (trace) {
+        fprintf(stderr, "[hb build] before the first batch: zero-vector scan %.3f s, build arrays %.3f s, workspaces %.3f s\n",
+                t_todo - t_enter, t_arrays - t_todo, t_begin - t_arrays);
         fprintf(stderr, "[hb build] device time: search %.3f s, select %.3f s, commit+edges+sort %.3f s, link %.3f s\n",
                 t_dev[0], t_dev[1], t_dev[2], t_dev[3]);
         for (auto &e : tev) cudaEventDestroy(e);

@@ -107,6 +107,8 @@ struct hb_index {
     hb::ScanWs *last_ws = nullptr;
     hb::DevBuf ws_build[12];
     int32_t *h_flag = nullptr;                // pinned: per-batch flag word of the build pipeline
+    cudaStream_t up_stream = nullptr;         // build: rows are uploaded ahead of the batch that indexes them
+    cudaEvent_t up_event = nullptr;
     unsigned long long *d_totals = nullptr;   // n_dist, n_hop0, n_hopu, n_slow, n_pair, ...
     hb_counters host_totals = {0, 0, 0, 0, 0};
     bool timing_valid = false;
