@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "partitioned"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "partitioned", "build"])
     ap.add_argument("--rows", dest="n", type=int, default=1000000)
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--queries", dest="nq", type=int, default=10000)
@@ -194,6 +194,8 @@ def main():
     base_seed = 20260101 + 1
     if args.workload == "partitioned" and args.impl == "ours":
         return run_partitioned(args, pkg, torch, dev, rank, local_rank, world, hbm_peak, peak_kind)
+    if args.workload == "build" and args.impl == "ours":
+        return run_build(args, pkg, torch, dev, rank, local_rank, world, hbm_peak, peak_kind)
 
     # ---------------------------------------------------------------- data + index (untimed)
     t0 = time.time()
@@ -439,6 +441,86 @@ def run_reference(args, pkg, ix, x_host, q_eval, ef, rec, n, dim, nq, build_s):
     return 0
 
 
+def exact_topk_metric(x_dev, q_dev, k, metric):
+    """torch fp32 exact top-k for l2 / ip / cosine (checker for recall only)."""
+    import torch
+    x = x_dev.float()
+    q = q_dev.float()
+    if metric == "cosine":
+        x = torch.nn.functional.normalize(x, dim=1)
+        q = torch.nn.functional.normalize(q, dim=1)
+    xx = (x * x).sum(1) if metric == "l2" else None
+    out = []
+    for s in range(0, q.shape[0], 256):
+        sims = q[s:s + 256] @ x.T
+        if metric == "l2":
+            sims = 2 * sims - xx[None, :]
+        out.append(torch.topk(sims, k, dim=1).indices)
+    return torch.cat(out).cpu().numpy()
+
+
+def run_build(args, pkg, torch, dev, rank, local_rank, world, hbm_peak, peak_kind):
+    """configs[3] shape: HNSW index build, 1M x 1536 halfvec inner product by default, hash-partitioned
+    into --partitions partitions that the ranks build independently (no collective); then a merged
+    search at ef_search=40 checks recall of what was built.  `value` = rows / max-over-ranks build time."""
+    n, k, P = args.n, 10, args.partitions
+    dim = args.dim if args.dim != 768 else 1536
+    opclass = os.environ.get("HB_BUILD_OPCLASS", "halfvec_ip_ops")
+    half = opclass.startswith("halfvec")
+    metric = "ip" if "_ip_" in opclass else ("l2" if "_l2_" in opclass else "cosine")
+    x = gen_set(n, dim, 20260104, dev)
+    if metric == "ip":     # not normalised: norms ~ lognormal(sigma = 0.1)
+        x = x * torch.exp(0.1 * torch.randn((n, 1), device=dev, generator=torch.Generator(device=dev).manual_seed(5)))
+    xs = x.half() if half else x
+    x_host = xs.cpu().numpy()
+    q = gen_set(1000, dim, 20260104 + 1000, dev)
+    qs = q.half() if half else q
+    gt = exact_topk_metric(xs, qs, k, metric)
+    del x, xs
+    torch.cuda.empty_cache()
+    pix = pkg.PartitionedIndex(dim, opclass, P, 16, 64, capacity_per_partition=int(n / P * 1.1) + 1024, rank=rank, world=world,
+                               device=local_rank, seed=3)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pix.build(x_host)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    ctr = {"n_dist": 0, "n_pair": 0}
+    for ix in pix.parts.values():
+        c = ix.counters(reset=True)
+        ctr["n_dist"] += c["n_dist"]; ctr["n_pair"] += c["n_pair"]
+    tt = torch.tensor([build_s, float(ctr["n_dist"]), float(ctr["n_pair"])], device=dev, dtype=torch.float64)
+    if world > 1:
+        tmax = tt.clone()
+        torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.SUM)
+        build_s = float(tmax[0].item())
+    n_dist, n_pair = float(tt[1].item()), float(tt[2].item())
+    t, d = pix.search_dev(qs, k, 40)
+    rec = recall_at(t.cpu().numpy(), gt)
+    row_bytes = dim * (2 if half else 4)
+    alg = (n_dist + n_pair) * row_bytes
+    if rank == 0:
+        print(json.dumps({"metric": "HNSW build vectors/s", "value": round(n / build_s, 1), "unit": "vectors/s", "n_gpus": world,
+                          "steps": 1, "warmup": 0, "ms_per_step": round(build_s * 1e3, 1), "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f16" if half else "f32", "data": "synthetic",
+                          "config": {"workload": "configs[3]: %dx%d %s index build, m=16, ef_construction=64, %d hash partitions "
+                                                 "built independently by %d rank(s), host rows in, no collective" % (n, dim, opclass, P, world),
+                                     "parallelism": "partitions/%d" % world, "recall@10_ef40_merged": round(rec, 4)},
+                          "roofline": {"bound": "hbm", "achieved": round(alg / build_s / 1e9 / world, 1), "peak": hbm_peak, "unit": "GB/s",
+                                       "frac": round(alg / build_s / 1e9 / world / hbm_peak, 4), "traffic": None, "peak_kind": peak_kind,
+                                       "note": "algorithmic bytes = (n_dist + n_pair) x row, the sequential algorithm's evaluations "
+                                               "(oracle counters), per GPU; the link phase memoises pair distances, so fewer rows are "
+                                               "actually fetched and the figure can exceed the HBM peak",
+                                       "n_dist_per_insert": round(n_dist / n, 1), "n_pair_per_insert": round(n_pair / n, 1)},
+                          "gpu_launches": None}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
 def run_partitioned(args, pkg, torch, dev, rank, local_rank, world, hbm_peak, peak_kind):
     """configs[2] shape: P hash partitions over the ranks, queries broadcast, NCCL all-gather of the
     per-rank top-k, merge.  Default sizes are scaled by --n (total rows)."""
@@ -446,10 +528,18 @@ def run_partitioned(args, pkg, torch, dev, rank, local_rank, world, hbm_peak, pe
     ef = args.ef if args.ef > 0 else 40
     pix = pkg.PartitionedIndex(dim, "vector_l2_ops" if dim == 128 else "vector_cosine_ops", P, 16, 64,
                                capacity_per_partition=int(n / P * 1.1) + 1024, rank=rank, world=world, device=local_rank, seed=3)
-    x = gen_set(n, dim, 20260103, dev).cpu().numpy()
+    x_dev = gen_set(n, dim, 20260103, dev)
+    q_eval = gen_set(1000, dim, 20260103 + 500, dev)
+    gt = exact_topk_metric(x_dev, q_eval, k, "l2" if dim == 128 else "cosine")
+    x = x_dev.cpu().numpy()
+    del x_dev
     t0 = time.time()
     pix.build(x)
     build_s = time.time() - t0
+    te, _ = pix.search_dev(q_eval, k, ef)
+    rec = recall_at(te.cpu().numpy(), gt)
+    for ix in pix.parts.values():
+        ix.counters(reset=True)
     total_steps = args.warmup + args.steps
     q_all = gen_set(nq * total_steps, dim, 20260103 + 1000, dev).view(total_steps, nq, dim)   # same on every rank = broadcast
     for w in range(args.warmup):
@@ -470,14 +560,25 @@ def run_partitioned(args, pkg, torch, dev, rank, local_rank, world, hbm_peak, pe
         tt = torch.tensor([ms], device=dev)
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
         ms = float(tt.item())
+    cs = [ix.counters(reset=True) for ix in pix.parts.values()]
+    row_bytes = dim * 4
+    alg = sum(c["n_dist"] * row_bytes + c["n_hop0"] * 128 + c["n_hopu"] * 64 for c in cs) + len(cs) * nq * args.steps * row_bytes
+    at = torch.tensor([float(alg)], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(at, op=torch.distributed.ReduceOp.SUM)
+    alg_gbs_per_gpu = float(at.item()) / (ms / 1e3) / 1e9 / world
     if rank == 0:
         print(json.dumps({"metric": "QPS (hash-partitioned, %d partitions, merged top-%d)" % (P, k), "value": round(nq * args.steps / (ms / 1e3), 1),
                           "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": "partitioned: %dx%d in %d hash partitions, ef_search=%d, queries broadcast, "
-                                                 "all-gather + merge" % (n, dim, P, ef), "parallelism": "partitions/%d" % world},
-                          "build": {"seconds": round(build_s, 2), "vectors_per_s": round(pix.n_local * world / build_s, 1)},
+                                                 "all-gather + merge" % (n, dim, P, ef), "parallelism": "partitions/%d" % world,
+                                     "recall@10": round(rec, 4)},
+                          "roofline": {"bound": "hbm", "achieved": round(alg_gbs_per_gpu, 1), "peak": hbm_peak, "unit": "GB/s",
+                                       "frac": round(alg_gbs_per_gpu / hbm_peak, 4), "traffic": None, "peak_kind": peak_kind,
+                                       "note": "per GPU; every query visits every partition, so the step does P searches per query"},
+                          "build": {"seconds": round(build_s, 2), "vectors_per_s": round(n / build_s, 1)},
                           "gpu_launches": args.steps * (len(pix.owned) * 4 + 2)}))
     if world > 1:
         torch.distributed.destroy_process_group()
