@@ -186,7 +186,7 @@ cudaError_t launch_scan_variant(const ScanParams &p, int num_sms, int max_grid, 
 
 // pick the chunks-per-lane specialisation: rows of exactly 32*NV 16-byte chunks get the unrolled
 // kernels (NV, rows in flight G, min CTAs per SM); any other row length runs the generic loop.
-#define HB_NV_TABLE(X) X(1, 8, 5) X(2, 8, 4) X(3, 4, 4) X(4, 4, 4) X(6, 4, 4) X(8, 2, 4)
+#define HB_NV_TABLE(X) X(1, 8, 6) X(2, 8, 4) X(3, 4, 4) X(4, 4, 4) X(6, 4, 4) X(8, 2, 4)
 inline int nv_of(int nvec)
 {
     if (nvec % 32) return 0;
@@ -207,6 +207,14 @@ cudaError_t launch_scan_t(const ScanParams &p, int num_sms, int max_grid, cudaSt
             case 3: return launch_scan_variant<T, IP, 6, 2, false, 5>(p, num_sms, max_grid, stream, info);
             case 4: return launch_scan_variant<T, IP, 6, 2, false, 6>(p, num_sms, max_grid, stream, info);
             case 5: return launch_scan_variant<T, IP, 6, 1, false, 6>(p, num_sms, max_grid, stream, info);
+            default: break;
+            }
+        }
+        if (nv_of(p.g.nvec) == 1 && p.variant) {
+            switch (p.variant) {
+            case 1: return launch_scan_variant<T, IP, 1, 8, false, 8>(p, num_sms, max_grid, stream, info);
+            case 2: return launch_scan_variant<T, IP, 1, 4, false, 8>(p, num_sms, max_grid, stream, info);
+            case 3: return launch_scan_variant<T, IP, 1, 8, false, 5>(p, num_sms, max_grid, stream, info);
             default: break;
             }
         }

@@ -74,28 +74,43 @@ class PartitionedIndex:
     # ---- search
     def search_local_dev(self, q_dev, k, ef_search):
         """q_dev: CUDA tensor nq x dim of the index dtype on this rank's GPU.  Returns this rank's
-        merged (tids, dist) CUDA tensors, nq x k."""
+        merged (tids, dist) CUDA tensors, nq x k.  The owned partitions are searched on up to four
+        CUDA streams at once (the drain of one partition's scan overlaps the ramp of the next), then
+        merged on the caller's stream."""
         import torch
         nq = q_dev.shape[0]
         dev = q_dev.device
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        main = torch.cuda.current_stream(dev)
         npart = len(self.parts)
-        tids = torch.full((max(npart, 1), nq, k), -1, dtype=torch.int64, device=dev)
-        dist = torch.full((max(npart, 1), nq, k), float("inf"), dtype=torch.float32, device=dev)
-        elem = torch.empty((nq, ef_search), dtype=torch.int32, device=dev)
-        edist = torch.empty((nq, ef_search), dtype=torch.float32, device=dev)
-        cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+        key = (nq, k, ef_search, str(dev))
+        if getattr(self, "_buf_key", None) != key:
+            n1 = max(npart, 1)
+            self._bufs = (torch.empty((n1, nq, k), dtype=torch.int64, device=dev), torch.empty((n1, nq, k), dtype=torch.float32, device=dev),
+                          torch.empty((n1, nq, ef_search), dtype=torch.int32, device=dev),
+                          torch.empty((n1, nq, ef_search), dtype=torch.float32, device=dev),
+                          torch.empty((n1, nq), dtype=torch.int32, device=dev),
+                          torch.empty((nq, k), dtype=torch.int64, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev))
+            self._buf_key = key
+        if not getattr(self, "_streams", None):
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(4, npart)))]
+        tids, dist, elem, edist, cnt, out_t, out_d = self._bufs
+        tids.fill_(-1)
+        dist.fill_(float("inf"))
+        for st in self._streams:
+            st.wait_stream(main)
         for i, ix in enumerate(self.parts.values()):
             if ix.n == 0:
                 continue
-            ix.search_dev(q_dev.data_ptr(), nq, ef_search, elem.data_ptr(), edist.data_ptr(), cnt.data_ptr(), stream)
-            ix.elements_to_tids_dev(elem.data_ptr(), edist.data_ptr(), nq, ef_search, k, tids[i].data_ptr(),
-                                    dist[i].data_ptr(), stream)
+            st = self._streams[i % len(self._streams)].cuda_stream
+            ix.search_dev(q_dev.data_ptr(), nq, ef_search, elem[i].data_ptr(), edist[i].data_ptr(), cnt[i].data_ptr(), st)
+            ix.elements_to_tids_dev(elem[i].data_ptr(), edist[i].data_ptr(), nq, ef_search, k, tids[i].data_ptr(),
+                                    dist[i].data_ptr(), st)
+        for st in self._streams:
+            main.wait_stream(st)
         if npart <= 1:
             return tids[0], dist[0]
-        out_t = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        merge_topk_dev(self.device, tids.data_ptr(), dist.data_ptr(), npart, nq, k, out_t.data_ptr(), out_d.data_ptr(), stream)
+        merge_topk_dev(self.device, tids.data_ptr(), dist.data_ptr(), npart, nq, k, out_t.data_ptr(), out_d.data_ptr(),
+                       main.cuda_stream)
         return out_t, out_d
 
     def exchange(self, local_tids, local_dist):
