@@ -80,12 +80,16 @@ int hb_index_entry(const hb_index *ix, int32_t *entry, int *entry_level);
  * skipped under HB_COSINE.  Returns the number of tuples indexed, or a negative error. */
 int64_t hb_build(hb_index *ix, const void *host_vecs, int64_t n, const int64_t *heap_tids);
 int64_t hb_insert(hb_index *ix, const void *host_vecs, int64_t n, const int64_t *heap_tids);
-/* batch size of the GPU insert pipeline (0 = automatic) */
+/* largest batch of the GPU insert pipeline (0 = automatic: min(8192, n/16); 1 = the sequential
+ * algorithm, graph identical to one-at-a-time insertion) */
 int hb_set_build_batch(hb_index *ix, int max_batch);
 /* HnswInitElement's level draw for the seq-th initialised element: (int)(-ln(U) / ln(m)), capped */
 int hb_level_for(uint64_t seed, int64_t seq, int m);
 /* tuning knobs: "slots" (visited-table size), "grid" (CTA cap), "build_batch",
- * "per_query_counters" (0/1).  0 restores the automatic choice. */
+ * "per_query_counters" (0/1), "variant" (scan kernel tuning variant), "link_kernel" (reverse-link
+ * kernel: 0 automatic, 1 warp per list, 2 pipelined TMA-staged, 3 memoised pair distances; all give
+ * the same graph), "pair_cache" (0 = do not allocate the pair-distance cache), "pair_fill" (0 = fill
+ * the cache in place instead of with the pre-pass).  0 restores the automatic choice. */
 int hb_set_option(hb_index *ix, const char *name, int value);
 
 /* ---- flat graph image (the layout in HBM; DESIGN.md "Data layout") ------------------------- */
