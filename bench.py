@@ -350,7 +350,11 @@ def main():
                        "l2_policy": "inputs larger than L2: graph+vectors %.2f GB, a distinct query batch every step" % ((n * row_bytes + n * 128) / 1e9),
                        "parity": "unpinned (reference mount has no source); ids bit-identical to oracle/ in tests"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                         "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_kind": peak_kind,
+                         "frac": round(achieved / hbm_peak, 4),
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one scan_kernel launch of this workload
+                         # (10 000 queries, ef_search=100) from profiles/r1_v3_scan_kernel_ncu_summary.txt
+                         "traffic": 13080542432 if (n, dim, nq, ef) == (1000000, 768, 10000, 100) else None,
+                         "peak_kind": peak_kind,
                          "frac_of_nominal_8000": round(achieved / 8000.0, 4),
                          "algorithmic_bytes_per_launch": int(alg_per_launch), "kernel": "scan_kernel (batched HnswSearchLayer)",
                          "last_launch_ms": round(last_kernel_ms, 4),

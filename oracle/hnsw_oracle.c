@@ -321,13 +321,49 @@ static Cand w_pop(Scratch *s)
 /* ep: entry candidates with distances already computed.  out: up to ef results, NEAREST first
  * (upstream returns the list furthest-first and consumes it from the tail; callers here index
  * from the front).  Returns the count. */
-static int search_layer(const OrcIndex *ix, const float *q, const Cand *ep, int nep, int ef, int lc,
-                        Cand *out, Scratch *s, OrcCounters *ctr)
+/* discarded candidates of an iterative scan (pgvector 0.8 HnswSearchLayer `discarded`): a min-heap
+ * on (distance, id) of everything that was visited but is not in W */
+typedef struct { Cand *a; int n, cap; } Disc;
+static void disc_push(Disc *h, Cand c)
 {
-    scratch_begin(s, ix->n, ef > nep ? ef : nep);
+    if (h->n == h->cap) { h->cap = h->cap ? 2 * h->cap : 1024; h->a = (Cand *) realloc(h->a, sizeof(Cand) * h->cap); }
+    int i = h->n++;
+    while (i > 0) { int p = (i - 1) / 2; if (!key_lt(c, h->a[p])) break; h->a[i] = h->a[p]; i = p; }
+    h->a[i] = c;
+}
+static Cand disc_pop(Disc *h)
+{
+    Cand top = h->a[0], last = h->a[--h->n];
+    int i = 0;
+    for (;;) {
+        int l = 2 * i + 1, r = l + 1, b = i; Cand bv = last;
+        if (l < h->n && key_lt(h->a[l], bv)) { b = l; bv = h->a[l]; }
+        if (r < h->n && key_lt(h->a[r], bv)) { b = r; bv = h->a[r]; }
+        if (b == i) break;
+        h->a[i] = h->a[b]; i = b;
+    }
+    if (h->n > 0) h->a[i] = last;
+    return top;
+}
+
+/* disc (nullable): evicted and not-admitted candidates are kept.  init_visited = 0: the visited set
+ * of the previous call stays and the entry points are not re-marked (ResumeScanItems).  tuples
+ * (nullable) counts visited elements as upstream's `tuples` does. */
+static int search_layer_ex(const OrcIndex *ix, const float *q, const Cand *ep, int nep, int ef, int lc,
+                           Cand *out, Scratch *s, OrcCounters *ctr, Disc *disc, int init_visited, int64_t *tuples)
+{
+    if (init_visited) scratch_begin(s, ix->n, ef > nep ? ef : nep);
+    else {
+        int need = (ef > nep ? ef : nep) + 2;
+        if (s->capW < need) { s->capW = need; s->W = (Cand *) realloc(s->W, sizeof(Cand) * s->capW); }
+        s->nC = s->nW = 0;
+    }
     int wlen = 0;
     for (int i = 0; i < nep; i++) {
-        s->stamp[ep[i].id] = s->epoch;
+        if (init_visited) {
+            s->stamp[ep[i].id] = s->epoch;
+            if (tuples) (*tuples)++;
+        }
         c_push(s, ep[i]);
         w_push(s, ep[i]);
         wlen++;
@@ -343,22 +379,32 @@ static int search_layer(const OrcIndex *ix, const float *q, const Cand *ep, int 
             int32_t e = nb[i];
             if (s->stamp[e] == s->epoch) continue;
             s->stamp[e] = s->epoch;
+            if (tuples) (*tuples)++;
             int always = wlen < ef;
             f = s->W[0];
             float ed = dist_q_row(ix, q, row_of(ix, e));
             if (ctr) ctr->n_dist++;
+            Cand ec = { ed, e };
             if (ed < f.d || always) {
-                Cand ec = { ed, e };
                 c_push(s, ec);
                 w_push(s, ec);
                 wlen++;
-                if (wlen > ef) { w_pop(s); wlen--; }   /* upstream leaves wlen > ef; same effect */
-            }
+                if (wlen > ef) {                       /* upstream leaves wlen > ef; same effect */
+                    Cand d = w_pop(s); wlen--;
+                    if (disc) disc_push(disc, d);
+                }
+            } else if (disc) disc_push(disc, ec);
         }
     }
     int cnt = s->nW;
     for (int i = cnt - 1; i >= 0; i--) out[i] = w_pop(s);
     return cnt;
+}
+
+static int search_layer(const OrcIndex *ix, const float *q, const Cand *ep, int nep, int ef, int lc,
+                        Cand *out, Scratch *s, OrcCounters *ctr)
+{
+    return search_layer_ex(ix, q, ep, nep, ef, lc, out, s, ctr, NULL, 1, NULL);
 }
 
 /* ------------------------------------------------------------------ SelectNeighbors */
@@ -692,6 +738,77 @@ void orc_search_batch(const OrcIndex *ix, const void *queries, int64_t nq, int e
         free(w); scratch_free(&s);
     }
     if (ctr) { ctr->n_dist += nd; ctr->n_hop0 += h0; ctr->n_hopu += hu; }
+}
+
+/* ------------------------------------------------------------------ iterative scan (pgvector 0.8) */
+/* hnswscan.c with hnsw.iterative_scan on: GetScanItems keeps the discarded candidates and the
+ * visited set; when the ef_search results are consumed, ResumeScanItems seeds another layer-0
+ * search with the ef_search nearest discarded candidates.  Once `tuples` reaches
+ * hnsw.max_scan_tuples the remaining discarded candidates are handed out one per call. */
+struct OrcIter {
+    const OrcIndex *ix;
+    float *q;
+    int ef;
+    int64_t max_tuples, tuples;
+    Scratch s;
+    Disc disc;
+    int started;
+    OrcCounters ctr;
+};
+
+OrcIter *orc_iter_begin(const OrcIndex *ix, const void *query, int ef, int64_t max_scan_tuples)
+{
+    OrcIter *it = (OrcIter *) calloc(1, sizeof *it);
+    it->ix = ix; it->ef = ef; it->max_tuples = max_scan_tuples;
+    it->q = (float *) malloc(sizeof(float) * ix->dim);
+    query_as_float(ix, query, it->q);
+    scratch_init(&it->s);
+    return it;
+}
+
+int orc_iter_next(OrcIter *it, int32_t *out_elem, float *out_dist)
+{
+    const OrcIndex *ix = it->ix;
+    int ef = it->ef, n = 0;
+    Cand *w = (Cand *) malloc(sizeof(Cand) * (ef + 2));
+    if (!it->started) {
+        it->started = 1;
+        if (ix->entry >= 0) {
+            Cand ep[1], u[2];
+            ep[0].id = ix->entry;
+            ep[0].d = dist_q_row(ix, it->q, row_of(ix, ix->entry));
+            it->ctr.n_dist++;
+            for (int lc = ix->entry_level; lc >= 1; lc--) {
+                search_layer(ix, it->q, ep, 1, 1, lc, u, &it->s, &it->ctr);
+                ep[0] = u[0];
+            }
+            n = search_layer_ex(ix, it->q, ep, 1, ef, 0, w, &it->s, &it->ctr, &it->disc, 1, &it->tuples);
+        }
+    } else if (it->disc.n > 0) {
+        if (it->tuples >= it->max_tuples) {
+            w[0] = disc_pop(&it->disc);          /* return remaining tuples */
+            n = 1;
+        } else {
+            Cand *ep = (Cand *) malloc(sizeof(Cand) * ef);
+            int nep = 0;
+            while (nep < ef && it->disc.n > 0) ep[nep++] = disc_pop(&it->disc);
+            n = search_layer_ex(ix, it->q, ep, nep, ef, 0, w, &it->s, &it->ctr, &it->disc, 0, &it->tuples);
+            free(ep);
+        }
+    }
+    for (int i = 0; i < n; i++) { out_elem[i] = w[i].id; out_dist[i] = w[i].d; }
+    free(w);
+    return n;
+}
+
+int64_t orc_iter_tuples(const OrcIter *it) { return it->tuples; }
+int64_t orc_iter_discarded(const OrcIter *it) { return it->disc.n; }
+void orc_iter_counters(const OrcIter *it, OrcCounters *out) { *out = it->ctr; }
+
+void orc_iter_end(OrcIter *it)
+{
+    if (!it) return;
+    scratch_free(&it->s); free(it->disc.a); free(it->q); free(it);
 }
 
 int orc_search_layer(const OrcIndex *ix, const void *query, const int32_t *ep, int nep, int ef,

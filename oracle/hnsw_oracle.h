@@ -70,6 +70,18 @@ int orc_search_tids(const OrcIndex *ix, const void *query, int ef, int k, int64_
 void orc_search_batch(const OrcIndex *ix, const void *queries, int64_t nq, int ef, int32_t *out_elem,
                       float *out_dist, int32_t *out_cnt, OrcCounters *ctr, int threads);
 
+/* hnsw.iterative_scan (pgvector 0.8 hnswscan.c GetScanItems with `discarded` + ResumeScanItems):
+ * orc_iter_next returns the next batch of elements nearest-first -- first the ef results of
+ * GetScanItems, then one ResumeScanItems batch per call; after `tuples` reached max_scan_tuples the
+ * remaining discarded candidates come one per call.  0 = exhausted.  out_* hold ef entries. */
+typedef struct OrcIter OrcIter;
+OrcIter *orc_iter_begin(const OrcIndex *ix, const void *query, int ef, int64_t max_scan_tuples);
+int orc_iter_next(OrcIter *it, int32_t *out_elem, float *out_dist);
+int64_t orc_iter_tuples(const OrcIter *it);
+int64_t orc_iter_discarded(const OrcIter *it);
+void orc_iter_counters(const OrcIter *it, OrcCounters *out);
+void orc_iter_end(OrcIter *it);
+
 /* one HnswSearchLayer call on an explicit entry list (for unit tests of the layer kernel) */
 int orc_search_layer(const OrcIndex *ix, const void *query, const int32_t *ep, int nep, int ef,
                      int lc, int32_t *out_elem, float *out_dist, OrcCounters *ctr);

@@ -68,6 +68,16 @@ def lib():
     L.orc_search_layer.restype = C.c_int
     L.orc_search_layer.argtypes = [C.c_void_p, vp, i32p, C.c_int, C.c_int, C.c_int, i32p, f32p, C.POINTER(Counters)]
     L.orc_bruteforce.argtypes = [C.c_void_p, vp, C.c_int64, C.c_int, i32p, vp, C.c_int]
+    L.orc_iter_begin.restype = C.c_void_p
+    L.orc_iter_begin.argtypes = [C.c_void_p, vp, C.c_int, C.c_int64]
+    L.orc_iter_next.restype = C.c_int
+    L.orc_iter_next.argtypes = [C.c_void_p, i32p, f32p]
+    L.orc_iter_tuples.restype = C.c_int64
+    L.orc_iter_tuples.argtypes = [C.c_void_p]
+    L.orc_iter_discarded.restype = C.c_int64
+    L.orc_iter_discarded.argtypes = [C.c_void_p]
+    L.orc_iter_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+    L.orc_iter_end.argtypes = [C.c_void_p]
     L.orc_distance.restype = C.c_float
     L.orc_distance.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     L.orc_normalize.restype = C.c_int
@@ -201,6 +211,26 @@ class Index:
         c = Counters()
         n = lib().orc_search_layer(self._h, _p(q), _p(ep), len(ep), ef, lc, _p(e), _p(d), C.byref(c))
         return e[:n], d[:n], c.as_dict()
+
+    def iterate(self, q, ef, max_scan_tuples=20000, max_batches=1 << 30):
+        """hnsw.iterative_scan: list of (elements, distances) batches, the first being GetScanItems'
+        result and each later one a ResumeScanItems batch (or single leftover candidates once
+        max_scan_tuples was reached).  Also returns (tuples, counters)."""
+        q = self._q(q)
+        it = lib().orc_iter_begin(self._h, _p(q), ef, max_scan_tuples)
+        out = []
+        e = np.empty(ef + 2, np.int32)
+        d = np.empty(ef + 2, np.float32)
+        while len(out) < max_batches:
+            n = lib().orc_iter_next(it, _p(e), _p(d))
+            if n == 0:
+                break
+            out.append((e[:n].copy(), d[:n].copy()))
+        tuples = lib().orc_iter_tuples(it)
+        c = Counters()
+        lib().orc_iter_counters(it, C.byref(c))
+        lib().orc_iter_end(it)
+        return out, tuples, c.as_dict()
 
     def bruteforce(self, qs, k, threads=1):
         qs = self._q(qs)
