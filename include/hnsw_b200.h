@@ -111,6 +111,27 @@ int hb_rescan(hb_scan *scan, const void *host_query, int ef_search);
 /* next-nearest heap TID: 1 = produced, 0 = exhausted, <0 = error.  Forward scans only. */
 int hb_gettuple(hb_scan *scan, int64_t *heap_tid, float *distance);
 void hb_endscan(hb_scan *scan);
+/* hnsw.iterative_scan (pgvector 0.8): HB_ITER_OFF = amgettuple stops after the ef_search results;
+ * HB_ITER_RELAXED / HB_ITER_STRICT = when they are consumed the scan resumes from the candidates it
+ * discarded (ResumeScanItems) until the index is exhausted; after max_scan_tuples visited tuples
+ * the remaining discarded candidates are returned without further search.  STRICT drops tuples
+ * that are nearer than one already returned.  Call between hb_beginscan and the first hb_gettuple
+ * (it applies to every later hb_rescan of this scan). */
+enum { HB_ITER_OFF = 0, HB_ITER_RELAXED = 1, HB_ITER_STRICT = 2 };
+int hb_scan_set_iterative(hb_scan *scan, int mode, int64_t max_scan_tuples);
+
+/* ---- resumable scans, batched ---------------------------------------------------------------- */
+/* The same thing for nq queries at once.  hb_iter_next returns each query's next batch of elements
+ * nearest-first (elem/dist: nq x ef_search host arrays, padded with -1 / +inf; cnt: nq): first the
+ * GetScanItems result, then one ResumeScanItems batch per call, then -- past max_scan_tuples --
+ * the leftover candidates one per call.  Return value: total elements produced (0 = every scan is
+ * exhausted), negative on error.  State per query lives in HBM (visited bitmap of n bits and the
+ * discarded list); hb_iter_begin fails with HB_ENOMEM when nq of them do not fit. */
+typedef struct hb_iter hb_iter;
+hb_iter *hb_iter_begin(hb_index *ix, const void *host_queries, int64_t nq, int ef_search, int64_t max_scan_tuples);
+int64_t hb_iter_next(hb_iter *it, int32_t *elem, float *dist, int32_t *cnt);
+int hb_iter_tuples(hb_iter *it, int64_t *tuples /* nq: upstream's `tuples` counter */);
+void hb_iter_end(hb_iter *it);
 
 /* ---- batched scan (the extension a GPU needs: many amrescan+amgettuple at once) ------------ */
 /* host buffers in, host buffers out; H2D and D2H copies happen inside.  For each of nq queries

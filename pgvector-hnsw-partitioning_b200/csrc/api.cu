@@ -747,6 +747,17 @@ hb_scan *hb_beginscan(hb_index *ix)
     return sc;
 }
 
+int hb_scan_set_iterative(hb_scan *sc, int mode, int64_t max_scan_tuples)
+{
+    if (!sc || mode < HB_ITER_OFF || mode > HB_ITER_STRICT || max_scan_tuples < 1) {
+        set_error("hb_scan_set_iterative: bad argument");
+        return HB_EINVAL;
+    }
+    sc->iter_mode = mode;
+    sc->max_scan_tuples = max_scan_tuples;
+    return HB_OK;
+}
+
 int hb_rescan(hb_scan *sc, const void *host_query, int ef)
 {
     if (!sc || !host_query) { set_error("hb_rescan: NULL argument"); return HB_EINVAL; }
@@ -754,6 +765,8 @@ int hb_rescan(hb_scan *sc, const void *host_query, int ef)
     const size_t b = (size_t) sc->ix->dim * sc->ix->esize;
     sc->query.assign((const char *) host_query, (const char *) host_query + b);
     sc->ef = ef; sc->bound = true; sc->fetched = false; sc->cnt = 0; sc->pos = 0; sc->tid_pos = -1;
+    if (sc->iter) { hb_iter_end(sc->iter); sc->iter = nullptr; }
+    sc->have_prev = false;
     return HB_OK;
 }
 
@@ -762,30 +775,54 @@ int hb_gettuple(hb_scan *sc, int64_t *heap_tid, float *distance)
     if (!sc || !heap_tid) { set_error("hb_gettuple: NULL argument"); return HB_EINVAL; }
     if (!sc->bound) { set_error("hb_gettuple: cannot scan hnsw index without order (no hb_rescan)"); return HB_ESTATE; }
     hb_index *ix = sc->ix;
-    if (!sc->fetched) {
-        // first call: GetScanItems
-        sc->elem.resize(sc->ef); sc->dist.resize(sc->ef);
-        int32_t cnt = 0;
-        int rc = hb_search_batch_elements(ix, sc->query.data(), 1, sc->ef, sc->elem.data(), sc->dist.data(), &cnt);
-        if (rc) return rc;
-        sc->cnt = cnt; sc->pos = 0; sc->tid_pos = -1; sc->fetched = true;
-    }
-    while (sc->pos < sc->cnt) {
-        const int32_t e = sc->elem[sc->pos];
-        if (sc->tid_pos < 0) sc->tid_pos = ix->h_ntids[e];
-        if (sc->tid_pos > 0) {
-            sc->tid_pos--;
-            *heap_tid = ix->h_tids[(int64_t) e * HB_HEAPTIDS + sc->tid_pos];
-            if (distance) *distance = sc->dist[sc->pos];
-            if (sc->tid_pos == 0) { sc->pos++; sc->tid_pos = -1; }
-            return 1;
+    for (;;) {
+        if (!sc->fetched || (sc->pos >= sc->cnt && sc->iter)) {
+            // first call: GetScanItems; later, with hnsw.iterative_scan on: ResumeScanItems
+            if (!sc->fetched && ix->n == 0) { sc->fetched = true; sc->cnt = 0; return 0; }
+            sc->elem.resize(sc->ef); sc->dist.resize(sc->ef);
+            int32_t cnt = 0;
+            if (sc->iter_mode == HB_ITER_OFF) {
+                int rc = hb_search_batch_elements(ix, sc->query.data(), 1, sc->ef, sc->elem.data(), sc->dist.data(), &cnt);
+                if (rc) return rc;
+            } else {
+                if (!sc->iter) {
+                    sc->iter = hb_iter_begin(ix, sc->query.data(), 1, sc->ef, sc->max_scan_tuples);
+                    if (!sc->iter) return HB_ECUDA;
+                }
+                const int64_t got = hb_iter_next(sc->iter, sc->elem.data(), sc->dist.data(), &cnt);
+                if (got < 0) return (int) got;
+                if (got == 0) { hb_iter_end(sc->iter); sc->iter = nullptr; }
+            }
+            sc->cnt = cnt; sc->pos = 0; sc->tid_pos = -1; sc->fetched = true;
         }
-        sc->pos++; sc->tid_pos = -1;
+        while (sc->pos < sc->cnt) {
+            const int32_t e = sc->elem[sc->pos];
+            if (sc->tid_pos < 0) sc->tid_pos = ix->h_ntids[e];
+            if (sc->tid_pos > 0) {
+                const float d = sc->dist[sc->pos];
+                sc->tid_pos--;
+                const int64_t tid = ix->h_tids[(int64_t) e * HB_HEAPTIDS + sc->tid_pos];
+                if (sc->tid_pos == 0) { sc->pos++; sc->tid_pos = -1; }
+                if (sc->iter_mode == HB_ITER_STRICT) {
+                    if (sc->have_prev && d < sc->prev_dist) continue;       // out of order: dropped
+                    sc->prev_dist = d; sc->have_prev = true;
+                }
+                *heap_tid = tid;
+                if (distance) *distance = d;
+                return 1;
+            }
+            sc->pos++; sc->tid_pos = -1;
+        }
+        if (!sc->iter) return 0;
     }
-    return 0;
 }
 
-void hb_endscan(hb_scan *sc) { delete sc; }
+void hb_endscan(hb_scan *sc)
+{
+    if (!sc) return;
+    if (sc->iter) hb_iter_end(sc->iter);
+    delete sc;
+}
 
 // ---- opclass support functions ---------------------------------------------------------------
 int hb_distance_batch(hb_index *ix, const void *host_queries, int64_t nq, const int32_t *cand, int nc, float *out)

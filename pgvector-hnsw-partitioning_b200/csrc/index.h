@@ -123,8 +123,14 @@ struct hb_index {
     }
 };
 
+struct hb_iter;
 struct hb_scan {
     hb_index *ix = nullptr;
+    int iter_mode = 0;              // hnsw.iterative_scan: HB_ITER_*
+    int64_t max_scan_tuples = 20000;
+    hb_iter *iter = nullptr;
+    float prev_dist = 0.f;
+    bool have_prev = false;
     std::vector<char> query;
     int ef = 0;
     bool bound = false, fetched = false;

@@ -17,7 +17,9 @@ cudaError_t HB_CAT(dist_, HBI_NAME)(const DistBatchParams &p, cudaStream_t s) { 
 }   // namespace hb
 
 #include "build_kernel.cuh"
+#include "iter_kernel.cuh"
 namespace hb {
+cudaError_t HB_CAT(iter_, HBI_NAME)(const IterParams &p, int grid, cudaStream_t s) { return launch_iter_t<HBI_T, HBI_IP>(p, grid, s); }
 cudaError_t HB_CAT(build_search_, HBI_NAME)(const BuildSearchParams &p, int sms, int slow_grid, cudaStream_t s, bool slow)
 {
     return slow ? launch_build_search_t<HBI_T, HBI_IP, true>(p, sms, slow_grid, s)

@@ -150,10 +150,44 @@ struct VisitedBitmap {       // HBM, one bit per element (large-visited-set path
     __device__ __forceinline__ void added(int n_new, bool) { count += n_new; }
 };
 
+// ---- discarded candidates (hnsw.iterative_scan) ------------------------------------------------
+// pgvector 0.8's HnswSearchLayer can keep what it throws away -- candidates evicted from W and
+// candidates that were evaluated but not admitted -- so that the scan can be resumed from them
+// (hnswscan.c ResumeScanItems [RECALL]).  NoDiscard compiles to nothing.
+struct NoDiscard {
+    static constexpr bool enabled = false;
+    __device__ __forceinline__ void push1(float, uint32_t, int) {}
+    __device__ __forceinline__ void push_mask(unsigned, float, uint32_t, int) {}
+};
+struct DiscList {            // unsorted list in HBM, one per query; n is warp-uniform
+    static constexpr bool enabled = true;
+    float *d;
+    uint32_t *id;
+    int n, cap;
+    bool overflow;
+    __device__ __forceinline__ void push1(float dd, uint32_t i, int lane)
+    {
+        if (n < cap) { if (lane == 0) { d[n] = dd; id[n] = i; } }
+        else overflow = true;
+        n++;
+    }
+    // every lane flagged in `mask` contributes its (dd, i)
+    __device__ __forceinline__ void push_mask(unsigned mask, float dd, uint32_t i, int lane)
+    {
+        const int pos = n + __popc(mask & ((1u << lane) - 1u));
+        if ((mask >> lane) & 1u) {
+            if (pos < cap) { d[pos] = dd; id[pos] = i; }
+        }
+        n += __popc(mask);
+        if (n > cap) overflow = true;
+    }
+};
+
 // ---- W list ---------------------------------------------------------------------------------
 // insert (ed, eid) keeping key order; then trim to ef + boundary ties.  `low` = every entry below
 // it is expanded.
-__device__ __forceinline__ int wlist_insert(WList &w, float ed, uint32_t eid, int ef, int lane, int &low)
+template <typename DS>
+__device__ __forceinline__ int wlist_insert(WList &w, float ed, uint32_t eid, int ef, int lane, int &low, DS &ds)
 {
     if (w.L + 1 > w.cap) return ST_TAIL;
     int pos = 0;
@@ -191,10 +225,23 @@ __device__ __forceinline__ int wlist_insert(WList &w, float ed, uint32_t eid, in
             keep += run;
             if (run < 32) break;
         }
+        if constexpr (DS::enabled) {
+            // evicted from W for good: they go to the discarded list
+            for (int base = ef + keep; base < w.L; base += 32) {
+                const int i = base + lane;
+                const bool act = i < w.L;
+                ds.push_mask(__ballot_sync(FULL, act), act ? w.d[i] : 0.f, act ? (w.id[i] & ID_MASK) : 0u, lane);
+            }
+        }
         w.L = ef + keep;
     }
     if (pos < low) low = pos;
     return ST_OK;
+}
+__device__ __forceinline__ int wlist_insert(WList &w, float ed, uint32_t eid, int ef, int lane, int &low)
+{
+    NoDiscard nd;
+    return wlist_insert(w, ed, eid, ef, lane, low, nd);
 }
 
 // make the first min(L, keep) entries the entry list of the next HnswSearchLayer call: drop the
@@ -286,9 +333,9 @@ __device__ __forceinline__ void eval_candidates2(const GraphView &g, const float
 
 // HnswSearchLayer.  Precondition: w holds the entry candidates (sorted, unexpanded) and vs holds
 // exactly their ids.  Postcondition: w[0 .. min(L, ef)) = the result, nearest first.
-template <typename T, bool IP, int NV, int G, typename VS>
+template <typename T, bool IP, int NV, int G, typename VS, typename DS>
 __device__ __forceinline__ int search_layer(const GraphView &g, WList &w, VS &vs, const float *q, int ef, int lc,
-                                            int lane, QueryCounters &ctr)
+                                            int lane, QueryCounters &ctr, DS &ds)
 {
     const int deg = lc == 0 ? 2 * g.m : g.m;
     int low = 0;
@@ -324,18 +371,30 @@ __device__ __forceinline__ int search_layer(const GraphView &g, WList &w, VS &vs
             const bool full = w.L >= ef;
             const float f = full ? w.d[ef - 1] : 0.f;
             unsigned amask = __ballot_sync(FULL, isnew && (!full || myd < f));
+            if constexpr (DS::enabled) ds.push_mask(nmask & ~amask, myd, (uint32_t) nb, lane);   // evaluated, not admitted
             while (amask) {
                 const int s = __ffs(amask) - 1;
                 amask &= amask - 1;
                 const float ed = __shfl_sync(FULL, myd, s);
                 const uint32_t eid = (uint32_t) __shfl_sync(FULL, nb, s);
-                if (w.L >= ef && !(ed < w.d[ef - 1])) continue;
-                const int st = wlist_insert(w, ed, eid, ef, lane, low);
+                if (w.L >= ef && !(ed < w.d[ef - 1])) {
+                    if constexpr (DS::enabled) ds.push1(ed, eid, lane);
+                    continue;
+                }
+                const int st = wlist_insert(w, ed, eid, ef, lane, low, ds);
                 if (st) return st;
             }
         }
     }
     return ST_OK;
+}
+
+template <typename T, bool IP, int NV, int G, typename VS>
+__device__ __forceinline__ int search_layer(const GraphView &g, WList &w, VS &vs, const float *q, int ef, int lc,
+                                            int lane, QueryCounters &ctr)
+{
+    NoDiscard nd;
+    return search_layer<T, IP, NV, G, VS, NoDiscard>(g, w, vs, q, ef, lc, lane, ctr, nd);
 }
 
 // distance of the single element `e` (warp-uniform) to the staged query

@@ -77,6 +77,11 @@ _SIGS = {
     "hb_rescan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "hb_gettuple": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_endscan": (None, [C.c_void_p]),
+    "hb_scan_set_iterative": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
+    "hb_iter_begin": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64]),
+    "hb_iter_next": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_iter_tuples": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hb_iter_end": (None, [C.c_void_p]),
     "hb_search_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_search_batch_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_search_batch_wait": (C.c_int, [C.c_void_p, C.c_int]),
@@ -250,6 +255,10 @@ class HnswIndex:
     def beginscan(self):
         return HnswScan(self)
 
+    def iterate(self, queries, ef_search=40, max_scan_tuples=20000):
+        """hnsw.iterative_scan, batched: a resumable scan per query (see HnswIterator)."""
+        return HnswIterator(self, queries, ef_search, max_scan_tuples)
+
     def search(self, queries, k=10, ef_search=40):
         """Batched `ORDER BY col <op> $1 LIMIT k`: host arrays in, host arrays out."""
         q = self._vecs(queries)
@@ -369,6 +378,12 @@ class HnswScan:
         if not self._h:
             raise _err(self._L, "hb_beginscan")
 
+    def set_iterative(self, mode="relaxed_order", max_scan_tuples=20000):
+        """hnsw.iterative_scan = off | relaxed_order | strict_order, hnsw.max_scan_tuples"""
+        m = {"off": 0, "relaxed_order": 1, "strict_order": 2}[mode]
+        if self._L.hb_scan_set_iterative(self._h, m, max_scan_tuples) < 0:
+            raise _err(self._L, "hb_scan_set_iterative")
+
     def rescan(self, query, ef_search=40):
         q = self.index._vecs(query)
         if q.shape[0] != 1:
@@ -391,3 +406,39 @@ class HnswScan:
             self._h = None
 
     __del__ = endscan
+
+
+class HnswIterator:
+    """Batched resumable scans (hnsw.iterative_scan): next() returns (elem, dist, cnt), each query's
+    next batch of elements nearest-first, or None when every scan is exhausted."""
+
+    def __init__(self, index, queries, ef_search=40, max_scan_tuples=20000):
+        self.index = index
+        self._L = index._L
+        q = index._vecs(queries)
+        self.nq, self.ef = q.shape[0], ef_search
+        self._h = self._L.hb_iter_begin(index._h, _p(q), self.nq, ef_search, max_scan_tuples)
+        if not self._h:
+            raise _err(self._L, "hb_iter_begin")
+
+    def next(self):
+        e = np.empty((self.nq, self.ef), np.int32)
+        d = np.empty((self.nq, self.ef), np.float32)
+        c = np.empty(self.nq, np.int32)
+        got = self._L.hb_iter_next(self._h, _p(e), _p(d), _p(c))
+        if got < 0:
+            raise _err(self._L, "hb_iter_next")
+        return None if got == 0 else (e, d, c)
+
+    def tuples(self):
+        t = np.empty(self.nq, np.int64)
+        if self._L.hb_iter_tuples(self._h, _p(t)) < 0:
+            raise _err(self._L, "hb_iter_tuples")
+        return t
+
+    def close(self):
+        if self._h:
+            self._L.hb_iter_end(self._h)
+            self._h = None
+
+    __del__ = close
