@@ -31,7 +31,8 @@ extern "C" {
 enum {
     HB_L2 = 0,     /* vector_l2_ops / halfvec_l2_ops         : vector_l2_squared_distance       */
     HB_IP = 1,     /* vector_ip_ops / halfvec_ip_ops         : vector_negative_inner_product    */
-    HB_COSINE = 2  /* vector_cosine_ops / halfvec_cosine_ops : normalise (FUNCTION 2) + neg. ip */
+    HB_COSINE = 2, /* vector_cosine_ops / halfvec_cosine_ops : normalise (FUNCTION 2) + neg. ip */
+    HB_L1 = 3      /* vector_l1_ops / halfvec_l1_ops (0.7+)  : l1_distance (no exact scan)       */
 };
 enum { HB_F32 = 0 /* vector */, HB_F16 = 1 /* halfvec */ };
 

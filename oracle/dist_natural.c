@@ -49,6 +49,23 @@ float orc_nat_ip_f16(int dim, const float *ax, const uint16_t *bx)
     return distance;
 }
 
+/* VectorL1Distance / HalfvecL1Distance (pgvector 0.7+) */
+float orc_nat_l1_f32(int dim, const float *ax, const float *bx)
+{
+    float distance = 0.0f;
+    for (int i = 0; i < dim; i++)
+        distance += __builtin_fabsf(ax[i] - bx[i]);
+    return distance;
+}
+
+float orc_nat_l1_f16(int dim, const float *ax, const uint16_t *bx)
+{
+    float distance = 0.0f;
+    for (int i = 0; i < dim; i++)
+        distance += __builtin_fabsf(ax[i] - _cvtsh_ss(bx[i]));
+    return distance;
+}
+
 /* vector_norm / l2_normalize accumulate in double */
 double orc_nat_sqnorm_f32(int dim, const float *ax)
 {

@@ -36,6 +36,8 @@ float orc_nat_l2_f32(int dim, const float *ax, const float *bx);
 float orc_nat_ip_f32(int dim, const float *ax, const float *bx);
 float orc_nat_l2_f16(int dim, const float *ax, const uint16_t *bx);
 float orc_nat_ip_f16(int dim, const float *ax, const uint16_t *bx);
+float orc_nat_l1_f32(int dim, const float *ax, const float *bx);
+float orc_nat_l1_f16(int dim, const float *ax, const uint16_t *bx);
 double orc_nat_sqnorm_f32(int dim, const float *ax);
 
 typedef struct { float d; int32_t id; } Cand;
@@ -112,6 +114,17 @@ static float canon_ip(int dim, const float *a, const float *b, int vec)
     return canon_fold(acc, vec);
 }
 
+/* vector_l1_distance (pgvector 0.7 VectorL1Distance): sum of |a - b|, canonical order, plain adds */
+static float canon_l1(int dim, const float *a, const float *b, int vec)
+{
+    float acc[256];
+    int w = 32 * vec;
+    memset(acc, 0, sizeof(float) * w);
+    for (int e = 0; e < dim; e++)
+        acc[e % w] = acc[e % w] + fabsf(a[e] - b[e]);
+    return canon_fold(acc, vec);
+}
+
 /* squared norm in double, canonical order (products of two floats are exact in double, so only
  * the addition order matters) */
 static double canon_sqnorm(int dim, const float *a, int vec)
@@ -144,8 +157,17 @@ static void half_to_float(int dim, const uint16_t *h, float *f)
  * vector_l2_squared_distance / vector_negative_inner_product and halfvec equivalents) */
 static float dist_q_row(const OrcIndex *ix, const float *q, const void *row)
 {
-    int ip = ix->metric != ORC_L2;
+    int ip = ix->metric == ORC_IP || ix->metric == ORC_COSINE;
     float r;
+    if (ix->metric == ORC_L1) {
+        if (ix->dist_mode == ORC_DIST_NATURAL)
+            return ix->dtype == ORC_F32 ? orc_nat_l1_f32(ix->dim, q, (const float *) row)
+                                        : orc_nat_l1_f16(ix->dim, q, (const uint16_t *) row);
+        if (ix->dtype == ORC_F32) return canon_l1(ix->dim, q, (const float *) row, 4);
+        float tmp[ix->dim];
+        half_to_float(ix->dim, (const uint16_t *) row, tmp);
+        return canon_l1(ix->dim, q, tmp, 8);
+    }
     if (ix->dist_mode == ORC_DIST_NATURAL) {
         if (ix->dtype == ORC_F32)
             r = ip ? orc_nat_ip_f32(ix->dim, q, (const float *) row)
@@ -179,7 +201,8 @@ float orc_distance(int metric_is_ip, int dtype, int dist_mode, int dim, const vo
 {
     OrcIndex t;
     memset(&t, 0, sizeof t);
-    t.dim = dim; t.metric = metric_is_ip ? ORC_IP : ORC_L2; t.dtype = dtype; t.dist_mode = dist_mode;
+    /* 0 = l2, 1 = negative inner product, ORC_L1 = l1 */
+    t.dim = dim; t.metric = metric_is_ip == ORC_L1 ? ORC_L1 : (metric_is_ip ? ORC_IP : ORC_L2); t.dtype = dtype; t.dist_mode = dist_mode;
     float qa[dim];
     if (dtype == ORC_F32) memcpy(qa, a, sizeof(float) * dim);
     else half_to_float(dim, (const uint16_t *) a, qa);
@@ -853,6 +876,8 @@ void orc_bruteforce(const OrcIndex *ix, const void *queries, int64_t nq, int k, 
             double acc = 0.0;
             if (ix->metric == ORC_L2)
                 for (int i = 0; i < dim; i++) { double t = (double) q[i] - (double) r[i]; acc += t * t; }
+            else if (ix->metric == ORC_L1)
+                for (int i = 0; i < dim; i++) acc += fabs((double) q[i] - (double) r[i]);
             else {
                 for (int i = 0; i < dim; i++) acc += (double) q[i] * (double) r[i];
                 acc = -acc;

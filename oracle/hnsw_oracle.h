@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-enum { ORC_L2 = 0, ORC_IP = 1, ORC_COSINE = 2 };   /* vector_l2_ops / vector_ip_ops / vector_cosine_ops */
+enum { ORC_L2 = 0, ORC_IP = 1, ORC_COSINE = 2, ORC_L1 = 3 };   /* vector_l2_ops / vector_ip_ops / vector_cosine_ops / vector_l1_ops */
 enum { ORC_F32 = 0, ORC_F16 = 1 };                 /* vector / halfvec storage */
 /* distance summation order:
  *   ORC_DIST_CANON   = the fixed 32-lane x VEC-accumulator FMA order + butterfly tree the CUDA
@@ -91,7 +91,8 @@ int orc_search_layer(const OrcIndex *ix, const void *query, const int32_t *ep, i
 void orc_bruteforce(const OrcIndex *ix, const void *queries, int64_t nq, int k, int32_t *out_elem,
                     double *out_dist, int threads);
 
-/* scalar entry points (vector.c / halfutils.c support functions) */
+/* scalar entry points (vector.c / halfutils.c support functions); metric_is_ip: 0 = squared l2,
+ * 1 = negative inner product, ORC_L1 = l1 */
 float orc_distance(int metric_is_ip, int dtype, int dist_mode, int dim, const void *a, const void *b);
 /* l2_normalize; returns 0 if the norm is zero (HnswCheckNorm fails) */
 int orc_normalize(int dtype, int dist_mode, int dim, const void *in, void *out);

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libhnsw_oracle.so")
 
-L2, IP, COSINE = 0, 1, 2
+L2, IP, COSINE, L1 = 0, 1, 2, 3
 F32, F16 = 0, 1
 CANON, NATURAL = 0, 1
 HEAPTIDS = 10
@@ -109,7 +109,8 @@ def _np_dtype(dtype):
 def distance(a, b, metric=L2, dtype=F32, mode=CANON):
     a = np.ascontiguousarray(a, _np_dtype(dtype))
     b = np.ascontiguousarray(b, _np_dtype(dtype))
-    return float(lib().orc_distance(int(metric != L2), dtype, mode, a.shape[-1], _p(a), _p(b)))
+    code = L1 if metric == L1 else int(metric != L2)
+    return float(lib().orc_distance(code, dtype, mode, a.shape[-1], _p(a), _p(b)))
 
 
 def normalize(a, dtype=F32, mode=CANON):

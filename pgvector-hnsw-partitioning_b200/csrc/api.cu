@@ -155,18 +155,20 @@ __global__ void merge_topk_kernel(const int64_t *__restrict__ tids, const float 
     cudaError_t scan_fast_##name(const ScanParams &, int, int, cudaStream_t, ScanLaunchInfo *);               \
     cudaError_t scan_slow_##name(const ScanParams &, int, int, cudaStream_t, ScanLaunchInfo *);               \
     cudaError_t dist_##name(const DistBatchParams &, cudaStream_t);
-HB_DECL(f32_l2) HB_DECL(f32_ip) HB_DECL(f16_l2) HB_DECL(f16_ip)
+HB_DECL(f32_l2) HB_DECL(f32_ip) HB_DECL(f16_l2) HB_DECL(f16_ip) HB_DECL(f32_l1) HB_DECL(f16_l1)
 #undef HB_DECL
 
-scan_launch_fn get_scan_launcher(int dtype, bool ip, bool slow)
+scan_launch_fn get_scan_launcher(int dtype, int kind, bool slow)
 {
-    if (dtype == HB_F32) return ip ? (slow ? scan_slow_f32_ip : scan_fast_f32_ip) : (slow ? scan_slow_f32_l2 : scan_fast_f32_l2);
-    return ip ? (slow ? scan_slow_f16_ip : scan_fast_f16_ip) : (slow ? scan_slow_f16_l2 : scan_fast_f16_l2);
+    static const scan_launch_fn tab[2][3][2] = {
+        { { scan_fast_f32_l2, scan_slow_f32_l2 }, { scan_fast_f32_ip, scan_slow_f32_ip }, { scan_fast_f32_l1, scan_slow_f32_l1 } },
+        { { scan_fast_f16_l2, scan_slow_f16_l2 }, { scan_fast_f16_ip, scan_slow_f16_ip }, { scan_fast_f16_l1, scan_slow_f16_l1 } } };
+    return tab[dtype == HB_F32 ? 0 : 1][kind][slow ? 1 : 0];
 }
-dist_launch_fn get_dist_launcher(int dtype, bool ip)
+dist_launch_fn get_dist_launcher(int dtype, int kind)
 {
-    if (dtype == HB_F32) return ip ? dist_f32_ip : dist_f32_l2;
-    return ip ? dist_f16_ip : dist_f16_l2;
+    static const dist_launch_fn tab[2][3] = { { dist_f32_l2, dist_f32_ip, dist_f32_l1 }, { dist_f16_l2, dist_f16_ip, dist_f16_l1 } };
+    return tab[dtype == HB_F32 ? 0 : 1][kind];
 }
 
 constexpr int HB_OVERFLOW_SLOTS = 4096;
@@ -249,7 +251,7 @@ hb_index *hb_index_create(int device, int dim, int m, int efc, int metric, int d
                           uint64_t seed)
 {
     if (dim < 1 || dim > HB_MAX_DIM || m < 2 || m > 100 || efc < 4 || efc > 1000 || efc < 2 * m ||
-        metric < HB_L2 || metric > HB_COSINE || (dtype != HB_F32 && dtype != HB_F16) || capacity < 1 ||
+        metric < HB_L2 || metric > HB_L1 || (dtype != HB_F32 && dtype != HB_F16) || capacity < 1 ||
         capacity > 0x7ffffff0LL) {
         set_error("hb_index_create: invalid parameters (dim=%d m=%d ef_construction=%d metric=%d dtype=%d capacity=%lld)",
                   dim, m, efc, metric, dtype, (long long) capacity);
@@ -543,7 +545,7 @@ static int scan_dev(hb_index *ix, ScanWs &ws, const void *dev_queries, int64_t n
     HB_CK(ws.ovf.ensure(sizeof(uint32_t) * (size_t) ix->num_sms * MAX_CTAS_PER_SM * SCAN_WARPS * p.oslots));
     p.ovf = ws.ovf.as<uint32_t>();
 
-    const bool ip = ix->metric != HB_L2;
+    const int ip = metric_kind(ix->metric);
     HB_CK(cudaEventRecord(ws.ev0, s));
     p.work = misc + 0;
     ScanLaunchInfo info;
@@ -843,7 +845,7 @@ int hb_distance_batch(hb_index *ix, const void *host_queries, int64_t nq, const 
     if (rc) return rc;
     DistBatchParams p;
     p.g = ix->view(); p.queries = q; p.nq = nq; p.cand = ix->ws_elem.as<int32_t>(); p.nc = nc; p.out = ix->ws_dist.as<float>();
-    HB_CK(get_dist_launcher(ix->dtype, ix->metric != HB_L2)(p, s));
+    HB_CK(get_dist_launcher(ix->dtype, metric_kind(ix->metric))(p, s));
     HB_CK(cudaMemcpyAsync(out, ix->ws_dist.p, sizeof(float) * nq * nc, cudaMemcpyDeviceToHost, s));
     HB_CK(cudaStreamSynchronize(s));
     return HB_OK;
@@ -857,7 +859,7 @@ int hb_distance_batch_dev(hb_index *ix, const void *dev_queries, int64_t nq, con
     HB_CK(cudaSetDevice(ix->device));
     DistBatchParams p;
     p.g = ix->view(); p.queries = dev_queries; p.nq = nq; p.cand = dev_cand; p.nc = nc; p.out = dev_out;
-    HB_CK(get_dist_launcher(ix->dtype, ix->metric != HB_L2)(p, (cudaStream_t) stream));
+    HB_CK(get_dist_launcher(ix->dtype, metric_kind(ix->metric))(p, (cudaStream_t) stream));
     return HB_OK;
 }
 

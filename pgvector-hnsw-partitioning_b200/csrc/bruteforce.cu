@@ -518,6 +518,11 @@ int hb_bruteforce_ex(hb_index *ix, const void *host_queries, int64_t nq, int k, 
 {
     if (!ix || !host_queries || !out_elem || !out_dist || k < 1 || k > 128) { set_error("hb_bruteforce: bad argument (1 <= k <= 128)"); return HB_EINVAL; }
     if (nq <= 0) return HB_OK;
+    if (ix->metric == HB_L1) {
+        // the exact scan is a q.x contraction (bf16 GEMM + fp32 re-rank): squared L2, inner product and cosine only
+        set_error("hb_bruteforce: the exact scan supports the l2, ip and cosine operator classes, not l1");
+        return HB_EINVAL;
+    }
     HB_CK(cudaSetDevice(ix->device));
     cudaStream_t s = ix->stream;
     const int64_t n = ix->n;
@@ -628,7 +633,7 @@ int hb_bruteforce_ex(hb_index *ix, const void *host_queries, int64_t nq, int k, 
     // fp32 re-rank of every candidate in the canonical order, then select + certify
     DistBatchParams dp;
     dp.g = ix->view(); dp.queries = qexact; dp.nq = nq; dp.cand = st.cand_id.as<int32_t>(); dp.nc = (int) C; dp.out = st.cand_dist.as<float>();
-    HB_CK(get_dist_launcher(ix->dtype, ix->metric != HB_L2)(dp, s));
+    HB_CK(get_dist_launcher(ix->dtype, metric_kind(ix->metric))(dp, s));
     bf_select_kernel<<<(int) ((nq + 63) / 64), 64, 0, s>>>(st.cand_id.as<int32_t>(), st.cand_dist.as<float>(), st.cand_thr.as<float>(),
                                                           st.qnh.as<float>(), max_bits, (int) nq, S2, k, l2 ? 1 : 0,
                                                           st.out_elem.as<int32_t>(), st.out_dist.as<float>(), st.uncertain.as<int32_t>());
@@ -655,7 +660,7 @@ int hb_bruteforce_ex(hb_index *ix, const void *host_queries, int64_t nq, int k, 
             DistBatchParams fp;
             fp.g = ix->view(); fp.queries = (const char *) qexact + q * qrow; fp.nq = 1; fp.cand = st.iota.as<int32_t>();
             fp.nc = (int) n; fp.out = st.full_dist.as<float>();
-            HB_CK(get_dist_launcher(ix->dtype, ix->metric != HB_L2)(fp, s));
+            HB_CK(get_dist_launcher(ix->dtype, metric_kind(ix->metric))(fp, s));
             bf_full_select_kernel<<<1, 256, 0, s>>>(st.full_dist.as<float>(), n, k, st.out_elem.as<int32_t>() + q * k, st.out_dist.as<float>() + q * k);
             HB_CK(cudaGetLastError());
             HB_CK(cudaMemcpyAsync(out_elem + q * k, st.out_elem.as<int32_t>() + q * k, sizeof(int32_t) * k, cudaMemcpyDeviceToHost, s));

@@ -32,12 +32,12 @@ namespace hb {
     cudaError_t build_link_##name(const LinkParams &, int, int, cudaStream_t);                            \
     cudaError_t pair_fill_##name(const LinkParams &, int, int, cudaStream_t);                           \
     cudaError_t nbr_dist_##name(const NbrDistParams &, int, cudaStream_t);
-HB_DECLB(f32_l2) HB_DECLB(f32_ip) HB_DECLB(f16_l2) HB_DECLB(f16_ip)
+HB_DECLB(f32_l2) HB_DECLB(f32_ip) HB_DECLB(f16_l2) HB_DECLB(f16_ip) HB_DECLB(f32_l1) HB_DECLB(f16_l1)
 #undef HB_DECLB
 
 #define HB_PICK(fn, ix)                                                                                   \
-    ((ix)->dtype == HB_F32 ? ((ix)->metric != HB_L2 ? fn##_f32_ip : fn##_f32_l2)                          \
-                           : ((ix)->metric != HB_L2 ? fn##_f16_ip : fn##_f16_l2))
+    ((ix)->dtype == HB_F32 ? (metric_kind((ix)->metric) == 2 ? fn##_f32_l1 : metric_kind((ix)->metric) == 1 ? fn##_f32_ip : fn##_f32_l2) \
+                           : (metric_kind((ix)->metric) == 2 ? fn##_f16_l1 : metric_kind((ix)->metric) == 1 ? fn##_f16_ip : fn##_f16_l2))
 
 template <typename T>
 __global__ void normalize_rows_kernel(const T *__restrict__ in, char *__restrict__ out_rows, size_t row_bytes,

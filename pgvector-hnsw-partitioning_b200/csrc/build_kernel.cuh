@@ -47,7 +47,7 @@ template <typename T> __host__ __device__ inline size_t build_warp_smem(int nvec
     return (b + 15) & ~(size_t) 15;
 }
 
-template <typename T, bool IP, int NV, int G, bool SLOW>
+template <typename T, int IP, int NV, int G, bool SLOW>
 __global__ void __launch_bounds__(BUILD_WARPS * 32) build_search_kernel(const BuildSearchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_search_kernel(const Bu
 // cand_*: candidates nearest first (key order) in shared memory.  r_*: the selected list in
 // upstream's list order (furthest-first when nc <= lm, else selection order then back-fill).
 // `pruned` = the candidate upstream reports as pruned (-1 when nothing was dropped).
-template <typename T, bool IP, int NV, int G>
+template <typename T, int IP, int NV, int G>
 __device__ __forceinline__ int select_neighbors_warp(const GraphView &g, float *q, const int32_t *cand_id,
                                                      const float *cand_d, int nc, int lm, int32_t *r_id, float *r_d,
                                                      int32_t *wd_id, float *wd_d, int32_t &pruned, int lane,
@@ -211,7 +211,7 @@ template <typename T> __host__ __device__ inline size_t select_warp_smem(int nve
     return (b + 15) & ~(size_t) 15;
 }
 
-template <typename T, bool IP, int NV, int G>
+template <typename T, int IP, int NV, int G>
 __global__ void __launch_bounds__(BUILD_WARPS * 32) build_select_kernel(const BuildSelectParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_select_kernel(const Bu
 }
 
 // ---- HnswUpdateConnection, one warp per segment (see link_kernel.cuh) --------------------------
-template <typename T, bool IP, int NV, int G>
+template <typename T, int IP, int NV, int G>
 __global__ void __launch_bounds__(BUILD_WARPS * 32) link_warp_kernel(const LinkParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -374,7 +374,7 @@ template <typename T> __host__ __device__ inline size_t memo_warp_smem(int nvec,
 // per CTA: triangle index -> (a << 8 | b), so that a list's triangle moves with flat coalesced accesses
 __host__ __device__ inline size_t memo_lut_bytes(int lm0) { return ((size_t) lm0 * (lm0 - 1) / 2 * 2 + 15) & ~(size_t) 15; }
 
-template <typename T, bool IP, int NV, int G>
+template <typename T, int IP, int NV, int G>
 __global__ void __launch_bounds__(BUILD_WARPS * 32, 5) link_memo_kernel(const LinkParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -548,7 +548,7 @@ struct NbrDistParams {
     const int32_t *nbr; float *nbrd;
 };
 
-template <typename T, bool IP>
+template <typename T, int IP>
 __global__ void __launch_bounds__(BUILD_WARPS * 32) nbr_dist_kernel(const NbrDistParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) nbr_dist_kernel(const NbrDis
     default: CALL(0, 2); break;                                                                    \
     }
 
-template <typename T, bool IP, bool SLOW>
+template <typename T, int IP, bool SLOW>
 cudaError_t launch_build_search_t(const BuildSearchParams &p, int num_sms, int slow_grid, cudaStream_t stream)
 {
     cudaError_t err = cudaSuccess;
@@ -612,7 +612,7 @@ cudaError_t launch_build_search_t(const BuildSearchParams &p, int num_sms, int s
     return err;
 }
 
-template <typename T, bool IP>
+template <typename T, int IP>
 cudaError_t launch_build_select_t(const BuildSelectParams &p, int num_sms, cudaStream_t stream)
 {
     cudaError_t err = cudaSuccess;
@@ -638,7 +638,7 @@ cudaError_t launch_build_select_t(const BuildSelectParams &p, int num_sms, cudaS
 // which: 0 = automatic: the memoising kernel when the pair cache is allocated and m <= 31, else the
 // pipelined kernel when two stages of lm+1 rows fit shared memory, else the warp kernel;
 // 1 = warp kernel, 2 = pipelined kernel, 3 = memoising kernel (error when the choice cannot run)
-template <typename T, bool IP>
+template <typename T, int IP>
 cudaError_t launch_build_link_t(const LinkParams &p, int num_sms, int which, cudaStream_t stream)
 {
     cudaError_t err = cudaSuccess;
@@ -700,7 +700,7 @@ cudaError_t launch_build_link_t(const LinkParams &p, int num_sms, int which, cud
 // pair-cache fill pre-pass: link_pipe_kernel in fill mode over p.fill_list.  Returns
 // cudaErrorInvalidConfiguration when the pipelined kernel cannot run for this shape (the memoising
 // kernel then fills in place).
-template <typename T, bool IP>
+template <typename T, int IP>
 cudaError_t launch_pair_fill_t(const LinkParams &p, int num_sms, int max_items, cudaStream_t stream)
 {
     const int lm0 = 2 * p.g.m;
@@ -721,7 +721,7 @@ cudaError_t launch_pair_fill_t(const LinkParams &p, int num_sms, int max_items, 
     return cudaGetLastError();
 }
 
-template <typename T, bool IP>
+template <typename T, int IP>
 cudaError_t launch_nbr_dist_t(const NbrDistParams &p, int num_sms, cudaStream_t stream)
 {
     if (p.rows <= 0) return cudaSuccess;

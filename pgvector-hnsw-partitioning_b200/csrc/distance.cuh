@@ -1,4 +1,6 @@
 // distance.cuh -- warp-cooperative distance evaluation in the canonical summation order.
+// Template parameter IP selects the opclass FUNCTION 1: 0 = squared L2, 1 = negative inner product
+// (also cosine, on normalised rows), 2 = L1 (vector_l1_ops, pgvector 0.7 VectorL1Distance).
 //
 // Takes the role of pgvector's opclass FUNCTION 1 support functions: VectorL2SquaredDistance /
 // VectorInnerProduct (vector.c) and HalfvecL2SquaredDistance / HalfvecInnerProduct (halfutils.c)
@@ -41,18 +43,23 @@ template <> struct Vec<__half> { static constexpr int VEC = 8; };
 template <typename T> __device__ __forceinline__ int query_floats(int nvec) { return nvec * Vec<T>::VEC; }
 
 // one 16-byte chunk of a row against the matching query components (already in registers)
-template <typename T, bool IP>
+template <typename T, int IP>
 __device__ __forceinline__ void accum_chunk(float (&acc)[Vec<T>::VEC], const uint4 &raw, const float4 &qa,
                                             const float4 &qb)
 {
     if constexpr (sizeof(T) == 4) {
         const float v0 = __uint_as_float(raw.x), v1 = __uint_as_float(raw.y);
         const float v2 = __uint_as_float(raw.z), v3 = __uint_as_float(raw.w);
-        if constexpr (IP) {
+        if constexpr (IP == 1) {
             acc[0] = fmaf(qa.x, v0, acc[0]);
             acc[1] = fmaf(qa.y, v1, acc[1]);
             acc[2] = fmaf(qa.z, v2, acc[2]);
             acc[3] = fmaf(qa.w, v3, acc[3]);
+        } else if constexpr (IP == 2) {
+            acc[0] = acc[0] + fabsf(qa.x - v0);
+            acc[1] = acc[1] + fabsf(qa.y - v1);
+            acc[2] = acc[2] + fabsf(qa.z - v2);
+            acc[3] = acc[3] + fabsf(qa.w - v3);
         } else {
             float t;
             t = qa.x - v0; acc[0] = fmaf(t, t, acc[0]);
@@ -65,7 +72,16 @@ __device__ __forceinline__ void accum_chunk(float (&acc)[Vec<T>::VEC], const uin
         const float2 h1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
         const float2 h2 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.z));
         const float2 h3 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.w));
-        if constexpr (IP) {
+        if constexpr (IP == 2) {
+            acc[0] = acc[0] + fabsf(qa.x - h0.x);
+            acc[1] = acc[1] + fabsf(qa.y - h0.y);
+            acc[2] = acc[2] + fabsf(qa.z - h1.x);
+            acc[3] = acc[3] + fabsf(qa.w - h1.y);
+            acc[4] = acc[4] + fabsf(qb.x - h2.x);
+            acc[5] = acc[5] + fabsf(qb.y - h2.y);
+            acc[6] = acc[6] + fabsf(qb.z - h3.x);
+            acc[7] = acc[7] + fabsf(qb.w - h3.y);
+        } else if constexpr (IP == 1) {
             acc[0] = fmaf(qa.x, h0.x, acc[0]);
             acc[1] = fmaf(qa.y, h0.y, acc[1]);
             acc[2] = fmaf(qa.z, h1.x, acc[2]);
@@ -98,7 +114,7 @@ template <int VEC> __device__ __forceinline__ float fold_lane(const float (&a)[V
 // NV > 0: the row is exactly 32*NV chunks (every lane owns NV chunks; loads are issued
 // back-to-back from one base pointer per row with immediate offsets, G*NV 128-bit loads in flight
 // per lane); NV == 0: run-time loop for any row length.
-template <typename T, bool IP, int NV, int G>
+template <typename T, int IP, int NV, int G>
 __device__ __forceinline__ void group_partials(const char *__restrict__ vecs, uint32_t row_bytes, int nvec,
                                                const float *q, const int32_t (&ids)[G], int lane,
                                                float (&part)[G])
@@ -174,20 +190,20 @@ template <> struct XReduce<1> {
 };
 
 // distances of G candidates; result of candidate c is returned in every lane via out[c]
-template <typename T, bool IP, int NV, int G>
+template <typename T, int IP, int NV, int G>
 __device__ __forceinline__ float group_distance(const char *__restrict__ vecs, uint32_t row_bytes, int nvec,
                                                 const float *q, const int32_t (&ids)[G], int lane)
 {
     float part[G];
     group_partials<T, IP, NV, G>(vecs, row_bytes, nvec, q, ids, lane, part);
     const float s = XReduce<G>::run(part, lane, 16);
-    return IP ? -s : s;   // lane (c * 32/G) .. hold candidate c
+    return IP == 1 ? -s : s;   // lane (c * 32/G) .. hold candidate c
 }
 
 // Two queries at once: each candidate row is fetched once and accumulated against both staged
 // queries (same additions per (query, row) pair as group_distance).  Lane c*(32/G).. holds candidate
 // c's distance to q0 in out0 and to q1 in out1.
-template <typename T, bool IP, int NV, int G>
+template <typename T, int IP, int NV, int G>
 __device__ __forceinline__ void group_distance2(const char *__restrict__ vecs, uint32_t row_bytes, int nvec,
                                                 const float *q0, const float *q1, const int32_t (&ids)[G], int lane,
                                                 float &out0, float &out1)
@@ -248,12 +264,12 @@ __device__ __forceinline__ void group_distance2(const char *__restrict__ vecs, u
 #pragma unroll
     for (int c = 0; c < G; c++) { part0[c] = fold_lane<VEC>(acc0[c]); part1[c] = fold_lane<VEC>(acc1[c]); }
     const float s0 = XReduce<G>::run(part0, lane, 16), s1 = XReduce<G>::run(part1, lane, 16);
-    out0 = IP ? -s0 : s0;
-    out1 = IP ? -s1 : s1;
+    out0 = IP == 1 ? -s0 : s0;
+    out1 = IP == 1 ? -s1 : s1;
 }
 
 // distance between two rows staged in shared memory (stage_row layout), canonical order
-template <typename T, bool IP>
+template <typename T, int IP>
 __device__ __forceinline__ float staged_pair_distance(const float *q0, const float *q1, int nvec, int lane)
 {
     constexpr int VEC = Vec<T>::VEC;
@@ -273,13 +289,14 @@ __device__ __forceinline__ float staged_pair_distance(const float *q0, const flo
         }
 #pragma unroll
         for (int k = 0; k < VEC; k++) {
-            if constexpr (IP) acc[k] = fmaf(a[k], b[k], acc[k]);
+            if constexpr (IP == 1) acc[k] = fmaf(a[k], b[k], acc[k]);
+            else if constexpr (IP == 2) acc[k] = acc[k] + fabsf(a[k] - b[k]);
             else { const float t = a[k] - b[k]; acc[k] = fmaf(t, t, acc[k]); }
         }
     }
     float s = fold_lane<VEC>(acc);
     for (int b = 16; b >= 1; b >>= 1) s = s + __shfl_xor_sync(FULL, s, b);
-    return IP ? -s : s;
+    return IP == 1 ? -s : s;
 }
 
 // stage a query (global, index dtype, `dim` components) into shared memory as fp32 in the

@@ -144,11 +144,13 @@ namespace hb {
 struct ScanParams;
 struct ScanLaunchInfo;
 typedef cudaError_t (*scan_launch_fn)(const ScanParams &, int num_sms, int max_grid, cudaStream_t, ScanLaunchInfo *);
-scan_launch_fn get_scan_launcher(int dtype, bool ip, bool slow);
+// kind: 0 = squared L2, 1 = negative inner product (and cosine), 2 = L1 (metric_kind())
+scan_launch_fn get_scan_launcher(int dtype, int kind, bool slow);
 
 struct DistBatchParams;
 typedef cudaError_t (*dist_launch_fn)(const DistBatchParams &, cudaStream_t);
-dist_launch_fn get_dist_launcher(int dtype, bool ip);
+dist_launch_fn get_dist_launcher(int dtype, int kind);
+inline int metric_kind(int metric) { return metric == HB_L2 ? 0 : (metric == HB_L1 ? 2 : 1); }
 
 // api.cu: canonical l2_normalize of n rows resident in HBM
 int normalize_dev(hb_index *ix, const void *dev_in, int64_t n, void *dev_out, cudaStream_t s);

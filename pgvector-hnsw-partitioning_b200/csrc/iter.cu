@@ -19,13 +19,13 @@ struct hb_iter {
 
 namespace hb {
 #define HB_DECLI(name) cudaError_t iter_##name(const IterParams &, int, cudaStream_t);
-HB_DECLI(f32_l2) HB_DECLI(f32_ip) HB_DECLI(f16_l2) HB_DECLI(f16_ip)
+HB_DECLI(f32_l2) HB_DECLI(f32_ip) HB_DECLI(f16_l2) HB_DECLI(f16_ip) HB_DECLI(f32_l1) HB_DECLI(f16_l1)
 #undef HB_DECLI
 static cudaError_t launch_iter(const hb_index *ix, const IterParams &p, int grid, cudaStream_t s)
 {
-    const bool ip = ix->metric != HB_L2;
-    if (ix->dtype == HB_F32) return ip ? iter_f32_ip(p, grid, s) : iter_f32_l2(p, grid, s);
-    return ip ? iter_f16_ip(p, grid, s) : iter_f16_l2(p, grid, s);
+    const int kind = metric_kind(ix->metric);
+    if (ix->dtype == HB_F32) return kind == 2 ? iter_f32_l1(p, grid, s) : kind == 1 ? iter_f32_ip(p, grid, s) : iter_f32_l2(p, grid, s);
+    return kind == 2 ? iter_f16_l1(p, grid, s) : kind == 1 ? iter_f16_ip(p, grid, s) : iter_f16_l2(p, grid, s);
 }
 }   // namespace hb
 

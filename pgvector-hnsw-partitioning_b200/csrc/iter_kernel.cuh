@@ -67,7 +67,7 @@ __device__ __forceinline__ void disc_pop_min(DiscList &ds, int lane, float &out_
     out_d = bd; out_id = bi;
 }
 
-template <typename T, bool IP, int NV, int G>
+template <typename T, int IP, int NV, int G>
 __global__ void __launch_bounds__(SCAN_WARPS * 32) iter_scan_kernel(const IterParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) iter_scan_kernel(const IterPa
     }
 }
 
-template <typename T, bool IP>
+template <typename T, int IP>
 cudaError_t launch_iter_t(const IterParams &p, int grid, cudaStream_t stream)
 {
     cudaError_t err = cudaSuccess;

@@ -77,7 +77,7 @@ template <typename T> __device__ __forceinline__ void chunk_to_float(const uint4
 
 // distances of the TA x TB pairs (ia[x], ib[y]) of rows resident in shared memory; pair c = x*TB+y
 // is returned in lane c * (32 / (TA*TB)).  Same additions as group_distance (distance.cuh).
-template <typename T, bool IP, int TA, int TB>
+template <typename T, int IP, int TA, int TB>
 __device__ __forceinline__ float pair_tile(const char *rows, uint32_t row_bytes, int nvec, const int (&ia)[TA],
                                            const int (&ib)[TB], int lane)
 {
@@ -105,7 +105,8 @@ __device__ __forceinline__ float pair_tile(const char *rows, uint32_t row_bytes,
             for (int y = 0; y < TB; y++)
 #pragma unroll
                 for (int k = 0; k < VEC; k++) {
-                    if constexpr (IP) acc[x * TB + y][k] = fmaf(a[x][k], b[y][k], acc[x * TB + y][k]);
+                    if constexpr (IP == 1) acc[x * TB + y][k] = fmaf(a[x][k], b[y][k], acc[x * TB + y][k]);
+                    else if constexpr (IP == 2) acc[x * TB + y][k] = acc[x * TB + y][k] + fabsf(a[x][k] - b[y][k]);
                     else {
                         const float t = a[x][k] - b[y][k];
                         acc[x * TB + y][k] = fmaf(t, t, acc[x * TB + y][k]);
@@ -116,7 +117,7 @@ __device__ __forceinline__ float pair_tile(const char *rows, uint32_t row_bytes,
 #pragma unroll
     for (int c = 0; c < NP; c++) part[c] = fold_lane<VEC>(acc[c]);
     const float s = XReduce<NP>::run(part, lane, 16);
-    return IP ? -s : s;
+    return IP == 1 ? -s : s;
 }
 
 // -DHB_LINK_PROFILE: cycle accounting of the pipeline roles into totals[6..13] (experiments only)
@@ -215,7 +216,7 @@ __device__ __forceinline__ LinkStage link_stage_at(unsigned char *base, size_t r
 }
 
 // distances new element (slot lm) <-> list slots [cb*4, cb*4+4), written to both halves of D
-template <typename T, bool IP>
+template <typename T, int IP>
 __device__ __forceinline__ void link_new_row_tile(const LinkStage &st, uint32_t row_bytes, int nvec, int lm, int ld,
                                                   int cb, int lane)
 {
@@ -301,7 +302,7 @@ __device__ __forceinline__ int link_select_slot(const float *D, int ld, const in
 // The shared-memory pipe is saturated by the tile loads of the other warps, so this avoids chains
 // of dependent shared-memory reads: lane l owns candidate slots l and l+32 in registers, ranks come
 // from shuffles, matrix rows are read with independent loads.
-template <typename T, bool IP>
+template <typename T, int IP>
 __device__ __forceinline__ void link_finalize(const LinkParams &p, const LinkStage &st, int lane,
                                               unsigned long long &npair)
 {
@@ -353,7 +354,7 @@ __device__ __forceinline__ void link_finalize(const LinkParams &p, const LinkSta
     for (int a = lane; a < lm; a += 32) { gl[a] = st.l_id[a]; gld[a] = st.l_d[a]; }
 }
 
-template <typename T, bool IP>
+template <typename T, int IP>
 __global__ void __launch_bounds__(LINK_THREADS, 1) link_pipe_kernel(const LinkParams p, const int nstages)
 {
     constexpr int TA = LinkTile<T>::TA, TB = LINK_TB, NP = TA * TB;

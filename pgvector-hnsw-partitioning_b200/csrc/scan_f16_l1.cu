@@ -1,6 +1,6 @@
 #define HB_CAT_(a, b) a##b
 #define HB_CAT(a, b) HB_CAT_(a, b)
 #define HBI_T __half
-#define HBI_IP 0
-#define HBI_NAME f16_l2
+#define HBI_IP 2
+#define HBI_NAME f16_l1
 #include "inst_scan.cuh"

@@ -48,7 +48,7 @@ template <typename T> __host__ __device__ inline size_t scan_warp_smem(int nvec,
     return (b + 15) & ~(size_t) 15;
 }
 
-template <typename T, bool IP, int NV, int G, bool SLOW, int MINB>
+template <typename T, int IP, int NV, int G, bool SLOW, int MINB>
 __global__ void __launch_bounds__(SCAN_WARPS * 32, MINB) scan_kernel(const ScanParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, MINB) scan_kernel(const ScanP
 // host-side launch helper -------------------------------------------------------------------
 struct ScanLaunchInfo { int grid; size_t smem; int blocks_per_sm; };
 
-template <typename T, bool IP, int NV, int G, bool SLOW, int MINB>
+template <typename T, int IP, int NV, int G, bool SLOW, int MINB>
 cudaError_t launch_scan_variant(const ScanParams &p, int num_sms, int max_grid, cudaStream_t stream,
                                 ScanLaunchInfo *info)
 {
@@ -194,7 +194,7 @@ inline int nv_of(int nvec)
     return (nv == 1 || nv == 2 || nv == 3 || nv == 4 || nv == 6 || nv == 8) ? nv : 0;
 }
 
-template <typename T, bool IP, bool SLOW>
+template <typename T, int IP, bool SLOW>
 cudaError_t launch_scan_t(const ScanParams &p, int num_sms, int max_grid, cudaStream_t stream,
                           ScanLaunchInfo *info)
 {
@@ -237,7 +237,7 @@ struct DistBatchParams {
     float *out;            // nq x nc
 };
 
-template <typename T, bool IP, int NV, int G>
+template <typename T, int IP, int NV, int G>
 __global__ void __launch_bounds__(SCAN_WARPS * 32) dist_batch_kernel(const DistBatchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) dist_batch_kernel(const DistB
     }
 }
 
-template <typename T, bool IP>
+template <typename T, int IP>
 cudaError_t launch_dist_t(const DistBatchParams &p, cudaStream_t stream)
 {
     const size_t smem = scan_warp_smem<T>(p.g.nvec, 0, 0, true) * SCAN_WARPS;

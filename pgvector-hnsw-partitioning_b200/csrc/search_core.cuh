@@ -268,7 +268,7 @@ struct QueryCounters { int n_dist, n_hop0, n_hopu; };
 
 // distances of the lanes flagged in `mask` (each flagged lane holds a candidate id in nb);
 // result returned in the flagged lane, +inf elsewhere.
-template <typename T, bool IP, int NV, int G>
+template <typename T, int IP, int NV, int G>
 __device__ __forceinline__ float eval_candidates(const GraphView &g, const float *q, int32_t nb, unsigned mask,
                                                  int lane)
 {
@@ -300,7 +300,7 @@ __device__ __forceinline__ float eval_candidates(const GraphView &g, const float
 }
 
 // as eval_candidates, against two staged queries: each candidate row is fetched once
-template <typename T, bool IP, int NV, int G>
+template <typename T, int IP, int NV, int G>
 __device__ __forceinline__ void eval_candidates2(const GraphView &g, const float *q0, const float *q1, int32_t nb,
                                                  unsigned mask, int lane, float &d0, float &d1)
 {
@@ -333,7 +333,7 @@ __device__ __forceinline__ void eval_candidates2(const GraphView &g, const float
 
 // HnswSearchLayer.  Precondition: w holds the entry candidates (sorted, unexpanded) and vs holds
 // exactly their ids.  Postcondition: w[0 .. min(L, ef)) = the result, nearest first.
-template <typename T, bool IP, int NV, int G, typename VS, typename DS>
+template <typename T, int IP, int NV, int G, typename VS, typename DS>
 __device__ __forceinline__ int search_layer(const GraphView &g, WList &w, VS &vs, const float *q, int ef, int lc,
                                             int lane, QueryCounters &ctr, DS &ds)
 {
@@ -389,7 +389,7 @@ __device__ __forceinline__ int search_layer(const GraphView &g, WList &w, VS &vs
     return ST_OK;
 }
 
-template <typename T, bool IP, int NV, int G, typename VS>
+template <typename T, int IP, int NV, int G, typename VS>
 __device__ __forceinline__ int search_layer(const GraphView &g, WList &w, VS &vs, const float *q, int ef, int lc,
                                             int lane, QueryCounters &ctr)
 {
@@ -398,7 +398,7 @@ __device__ __forceinline__ int search_layer(const GraphView &g, WList &w, VS &vs
 }
 
 // distance of the single element `e` (warp-uniform) to the staged query
-template <typename T, bool IP, int NV>
+template <typename T, int IP, int NV>
 __device__ __forceinline__ float one_distance(const GraphView &g, const float *q, int32_t e, int lane)
 {
     const int32_t ids[1] = { e };

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libhnsw_b200.so")
 _CSRC = os.path.join(_HERE, "csrc")
 
-HB_L2, HB_IP, HB_COSINE = 0, 1, 2
+HB_L2, HB_IP, HB_COSINE, HB_L1 = 0, 1, 2, 3
 HB_F32, HB_F16 = 0, 1
 HB_HEAPTIDS = 10
 
@@ -28,6 +28,8 @@ OPCLASSES = {
     "halfvec_l2_ops": (HB_L2, HB_F16),
     "halfvec_ip_ops": (HB_IP, HB_F16),
     "halfvec_cosine_ops": (HB_COSINE, HB_F16),
+    "vector_l1_ops": (HB_L1, HB_F32),
+    "halfvec_l1_ops": (HB_L1, HB_F16),
 }
 
 

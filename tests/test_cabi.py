@@ -30,10 +30,10 @@ def test_binding_covers_header(pkg):
 
 
 def test_opclass_surface(pkg):
-    assert set(pkg.OPCLASSES) == {"vector_l2_ops", "vector_ip_ops", "vector_cosine_ops",
-                                  "halfvec_l2_ops", "halfvec_ip_ops", "halfvec_cosine_ops"}
+    assert set(pkg.OPCLASSES) == {"vector_l2_ops", "vector_ip_ops", "vector_cosine_ops", "vector_l1_ops",
+                                  "halfvec_l2_ops", "halfvec_ip_ops", "halfvec_cosine_ops", "halfvec_l1_ops"}
     with pytest.raises(pkg.HnswError):
-        pkg.HnswIndex(8, "vector_l1_ops")
+        pkg.HnswIndex(8, "bit_hamming_ops")          # bit / sparsevec operator classes are out of scope
 
 
 @pytest.mark.skipif(has_gpu(), reason="checks the no-device failure mode")

@@ -130,3 +130,30 @@ def test_search_layer_upper(oracle):
     assert lvl >= 1
     e, d, c = ix.search_layer(x[5], [ent], 1, lvl)
     assert len(e) == 1 and c["n_hopu"] >= 1
+
+
+def test_iterative_scan_properties(oracle):
+    """hnsw.iterative_scan restatement (orc_iter_*): the first batch is the plain scan, later batches
+    never repeat an element, a full iteration reaches everything the graph connects, and with
+    max_scan_tuples reached the leftovers come one at a time in distance order."""
+    O = oracle
+    x = clustered(2500, 24, 16, seed=11)
+    q = clustered(5, 24, 16, seed=12)
+    ix = O.Index(24, 8, 32, O.L2, O.F32, O.CANON, seed=2)
+    ix.build(x)
+    for qi in q:
+        e0, d0, _ = ix.search_elements(qi, 20)
+        full, tuples, ctr = ix.iterate(qi, 20, max_scan_tuples=10 ** 9)
+        assert (full[0][0] == e0).all() and (full[0][1] == d0).all()
+        alle = np.concatenate([b[0] for b in full])
+        assert len(set(alle.tolist())) == len(alle) >= 2400
+        assert tuples == len(alle)                       # every visited element is returned exactly once
+        for e, d in full:
+            assert (np.diff(d) >= 0).all()               # each batch nearest-first
+        capped, t2, _ = ix.iterate(qi, 20, max_scan_tuples=300)
+        assert t2 >= 300
+        tail = [b for b in capped if len(b[0]) == 1]
+        assert len(tail) >= 1
+        td = np.array([b[1][0] for b in capped[len(capped) - len(tail):]])
+        assert (np.diff(td) >= 0).all()                  # leftovers in distance order
+        assert sum(len(b[0]) for b in capped) == t2
