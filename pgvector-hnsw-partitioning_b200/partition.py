@@ -92,19 +92,31 @@ class PartitionedIndex:
                           torch.empty((nq, k), dtype=torch.int64, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev))
             self._buf_key = key
         if not getattr(self, "_streams", None):
-            self._streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(4, npart)))]
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
         tids, dist, elem, edist, cnt, out_t, out_d = self._bufs
         tids.fill_(-1)
         dist.fill_(float("inf"))
         for st in self._streams:
             st.wait_stream(main)
+        # work items = (partition, slice of the query batch): with few partitions per rank the batch
+        # is cut so that four scans are still in flight (one scan's drain overlaps another's ramp)
+        nchunk = max(1, min(4 // max(npart, 1), nq // 1024))
+        bounds = [nq * c // nchunk for c in range(nchunk + 1)]
+        esz = q_dev.element_size() * q_dev.shape[1]
+        item = 0
         for i, ix in enumerate(self.parts.values()):
             if ix.n == 0:
                 continue
-            st = self._streams[i % len(self._streams)].cuda_stream
-            ix.search_dev(q_dev.data_ptr(), nq, ef_search, elem[i].data_ptr(), edist[i].data_ptr(), cnt[i].data_ptr(), st)
-            ix.elements_to_tids_dev(elem[i].data_ptr(), edist[i].data_ptr(), nq, ef_search, k, tids[i].data_ptr(),
-                                    dist[i].data_ptr(), st)
+            for c in range(nchunk):
+                lo, hi = bounds[c], bounds[c + 1]
+                if hi <= lo:
+                    continue
+                st = self._streams[item % len(self._streams)].cuda_stream
+                item += 1
+                ix.search_dev(q_dev.data_ptr() + lo * esz, hi - lo, ef_search, elem[i, lo].data_ptr(), edist[i, lo].data_ptr(),
+                              cnt[i, lo:].data_ptr(), st)
+                ix.elements_to_tids_dev(elem[i, lo].data_ptr(), edist[i, lo].data_ptr(), hi - lo, ef_search, k,
+                                        tids[i, lo].data_ptr(), dist[i, lo].data_ptr(), st)
         for st in self._streams:
             main.wait_stream(st)
         if npart <= 1:
