@@ -81,7 +81,7 @@ int hb_index_entry(const hb_index *ix, int32_t *entry, int *entry_level);
  * skipped under HB_COSINE.  Returns the number of tuples indexed, or a negative error. */
 int64_t hb_build(hb_index *ix, const void *host_vecs, int64_t n, const int64_t *heap_tids);
 int64_t hb_insert(hb_index *ix, const void *host_vecs, int64_t n, const int64_t *heap_tids);
-/* largest batch of the GPU insert pipeline (0 = automatic: min(8192, n/16); 1 = the sequential
+/* largest batch of the GPU insert pipeline (0 = automatic: n/16, at most 8192, 16384 from 512k elements; 1 = the sequential
  * algorithm, graph identical to one-at-a-time insertion) */
 int hb_set_build_batch(hb_index *ix, int max_batch);
 /* HnswInitElement's level draw for the seq-th initialised element: (int)(-ln(U) / ln(m)), capped */

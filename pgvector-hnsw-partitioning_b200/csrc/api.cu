@@ -320,6 +320,7 @@ int hb_set_option(hb_index *ix, const char *name, int value)
     else if (!strcmp(name, "link_kernel")) ix->opt_link_kernel = value;
     else if (!strcmp(name, "pair_cache")) ix->opt_pair_cache = value;
     else if (!strcmp(name, "pair_fill")) ix->opt_pair_fill = value;
+    else if (!strcmp(name, "fused_select")) ix->opt_fused_select = value;
     else { set_error("hb_set_option: unknown option %s", name); return HB_EINVAL; }
     return HB_OK;
 }

@@ -38,6 +38,13 @@ struct BuildSearchParams {
     uint32_t *ovf; int oslots;    // fast path: per-warp visited overflow table in HBM
     uint32_t *gbits; int gwords;
     float *gwd; uint32_t *gwi; int gcap;
+    // fused selection (fuse != 0): SelectNeighbors runs on each layer's W as soon as that layer's
+    // search is done -- the selection work of finished elements fills the tail of the batch's search
+    // -- and the candidate lists are not written out
+    int fuse;
+    int32_t *sel0_id; float *sel0_d; int32_t *sel0_cnt;     // B x 2m
+    int32_t *selu_id; float *selu_d; int32_t *selu_cnt;     // UR x m
+    int32_t *dup;                                           // B x DUP_SLOTS
 };
 
 template <typename T> __host__ __device__ inline size_t build_warp_smem(int nvec, int capW, int slots, bool slow)
@@ -47,14 +54,34 @@ template <typename T> __host__ __device__ inline size_t build_warp_smem(int nvec
     return (b + 15) & ~(size_t) 15;
 }
 
+// per warp: build_warp_smem + the selection's scratch (candidate ids, pruned list, selected list)
+template <typename T> __host__ __device__ inline size_t bsearch_warp_smem(int nvec, int capW, int slots, bool slow, int efc, int lm0)
+{
+    return build_warp_smem<T>(nvec, capW, slots, slow) + (((size_t) efc * 12 + (size_t) lm0 * 8 + 15) & ~(size_t) 15);
+}
+
+template <typename T, int IP, int NV, int G>
+__device__ __forceinline__ int select_neighbors_warp(const GraphView &g, float *q, const int32_t *cand_id,
+                                                     const float *cand_d, int nc, int lm, int32_t *r_id, float *r_d,
+                                                     int32_t *wd_id, float *wd_d, int32_t &pruned, int lane,
+                                                     unsigned long long &npair);
+
 template <typename T, int IP, int NV, int G, bool SLOW>
 __global__ void __launch_bounds__(BUILD_WARPS * 32) build_search_kernel(const BuildSearchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const GraphView &g = p.g;
-    unsigned char *base = smem + build_warp_smem<T>(g.nvec, p.capW, p.slots, SLOW) * warp;
+    const int lm0 = 2 * g.m;
+    const size_t wbytes = bsearch_warp_smem<T>(g.nvec, p.capW, p.slots, SLOW, p.efc, lm0);
+    unsigned char *base = smem + wbytes * warp;
     float *q = reinterpret_cast<float *>(base);
+    int32_t *c_id = reinterpret_cast<int32_t *>(base + build_warp_smem<T>(g.nvec, p.capW, p.slots, SLOW));
+    int32_t *wd_id = c_id + p.efc;
+    float *wd_d = reinterpret_cast<float *>(wd_id + p.efc);
+    int32_t *r_id = reinterpret_cast<int32_t *>(wd_d + p.efc);
+    float *r_d = reinterpret_cast<float *>(r_id + lm0);
+    unsigned long long npair = 0;
     using VS = typename std::conditional<SLOW, VisitedBitmap, VisitedHash>::type;
     WList w;
     VS vs;
@@ -85,6 +112,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_search_kernel(const Bu
         __syncwarp();
 
         QueryCounters ctr = { 0, 0, 0 };
+        unsigned long long np_e = 0;      // pairs of this element's selections; counted once it completes
         int st = ST_OK;
         int level = p.level[i];
         const float d0 = one_distance<T, IP, NV>(g, q, g.entry, lane);
@@ -108,6 +136,44 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_search_kernel(const Bu
             if (st != ST_OK) break;
             keep = p.efc;
             const int cnt = min(w.L, p.efc);
+            if (p.fuse) {
+                // SelectNeighbors on this layer's candidates (W is only read: it is the next layer's entry list)
+                const int lm = lc == 0 ? lm0 : g.m;
+                const size_t row = lc == 0 ? (size_t) i : (size_t) p.ucand_row[i] + (lc - 1);
+                __syncwarp();
+                for (int j = lane; j < cnt; j += 32) c_id[j] = (int32_t) (w.id[j] & ID_MASK);
+                __syncwarp();
+                int32_t pruned;
+                const int nr = select_neighbors_warp<T, IP, NV, (G > 4 ? 4 : G)>(g, q, c_id, w.d, cnt, lm, r_id, r_d, wd_id, wd_d, pruned,
+                                                                                lane, np_e);
+                int32_t *oid = (lc == 0 ? p.sel0_id : p.selu_id) + row * lm;
+                float *od = (lc == 0 ? p.sel0_d : p.selu_d) + row * lm;
+                for (int j = lane; j < lm; j += 32) { oid[j] = j < nr ? r_id[j] : -1; od[j] = j < nr ? r_d[j] : 0.f; }
+                if (lane == 0) (lc == 0 ? p.sel0_cnt : p.selu_cnt)[row] = nr;
+                if (lc == 0) {
+                    // FindDuplicateInMemory: neighbours in stored order while byte-identical to the new row
+                    const uint4 *mine = reinterpret_cast<const uint4 *>(g.vecs + (size_t) (p.first + i) * g.row_bytes);
+                    int nd = 0;
+                    for (int j = 0; j < nr && nd < DUP_SLOTS; j++) {
+                        const uint4 *other = reinterpret_cast<const uint4 *>(g.vecs + (size_t) r_id[j] * g.row_bytes);
+                        bool same = true;
+                        for (int ch = lane; ch < g.nvec; ch += 32) {
+                            const uint4 a = mine[ch], b = other[ch];
+                            same = same && a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w;
+                        }
+                        if (!__all_sync(FULL, same)) break;
+                        if (lane == 0) p.dup[(size_t) i * DUP_SLOTS + nd] = r_id[j];
+                        nd++;
+                    }
+                    if (lane == 0 && nd < DUP_SLOTS) p.dup[(size_t) i * DUP_SLOTS + nd] = -1;
+                } else {
+                    // the selection staged candidate rows over the query: put the query back for the next layer
+                    __syncwarp();
+                    stage_row<T>(g.vecs + (size_t) (p.first + i) * g.row_bytes, g.nvec, q, lane);
+                    __syncwarp();
+                }
+                continue;
+            }
             int32_t *cid; float *cd;
             if (lc == 0) {
                 cid = p.cand0_id + (size_t) i * p.efc; cd = p.cand0_d + (size_t) i * p.efc;
@@ -127,6 +193,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_search_kernel(const Bu
             }
             continue;
         }
+        npair += np_e;
         if (lane == 0) {
             p.status[i] = st == ST_OK ? 0 : -st;
             atomicAdd(p.totals + 0, (unsigned long long) ctr.n_dist);
@@ -135,6 +202,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_search_kernel(const Bu
             if (SLOW) atomicAdd(p.totals + 3, 1ull);
         }
     }
+    if (lane == 0 && npair) atomicAdd(p.totals + 4, npair);
 }
 
 // ---- SelectNeighbors ------------------------------------------------------------------------
@@ -589,7 +657,7 @@ cudaError_t launch_build_search_t(const BuildSearchParams &p, int num_sms, int s
 #define HB_CALL(NVV, GG)                                                                           \
     {                                                                                              \
         auto kern = build_search_kernel<T, IP, SLOW ? 0 : NVV, SLOW ? 2 : GG, SLOW>;               \
-        const size_t smem = build_warp_smem<T>(p.g.nvec, p.capW, p.slots, SLOW) * BUILD_WARPS;     \
+        const size_t smem = bsearch_warp_smem<T>(p.g.nvec, p.capW, p.slots, SLOW, p.efc, 2 * p.g.m) * BUILD_WARPS; \
         err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
         if (err == cudaSuccess) {                                                                  \
             int bps = 0;                                                                           \
