@@ -100,6 +100,12 @@ int hb_set_option(hb_index *ix, const char *name, int value);
 int hb_index_load(hb_index *ix, int64_t n, int64_t upper_rows, int32_t entry, const void *vecs,
                   const uint8_t *level, const int32_t *nbr0, const int32_t *uoff,
                   const int32_t *nbru, const uint8_t *ntids, const int64_t *tids);
+/* Load the graph from the pages of a pgvector HNSW index relation as PostgreSQL stores them (n_pages
+ * x 8192 bytes: block 0 = metapage, then element / neighbour tuples; pgvector 0.7-0.8 layout AS
+ * RECALLED -- see csrc/pgpages.cu).  The handle's dim, m and dtype must match the index; vectors of
+ * a cosine index are stored normalised already.  Deleted elements keep their place in the graph
+ * and return no tuples. */
+int hb_index_load_pgvector_pages(hb_index *ix, const void *pages, int64_t n_pages);
 int64_t hb_index_upper_rows(const hb_index *ix);
 /* any pointer may be NULL */
 int hb_index_export(const hb_index *ix, void *vecs, uint8_t *level, int32_t *nbr0, int32_t *uoff,

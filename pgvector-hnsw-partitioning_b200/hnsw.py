@@ -74,6 +74,7 @@ _SIGS = {
     "hb_level_for": (C.c_int, [C.c_uint64, C.c_int64, C.c_int]),
     "hb_index_load": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32] + [C.c_void_p] * 7),
     "hb_index_upper_rows": (C.c_int64, [C.c_void_p]),
+    "hb_index_load_pgvector_pages": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "hb_index_export": (C.c_int, [C.c_void_p] + [C.c_void_p] * 7),
     "hb_beginscan": (C.c_void_p, [C.c_void_p]),
     "hb_rescan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
@@ -232,6 +233,13 @@ class HnswIndex:
                 np.ascontiguousarray(g.ntids, np.uint8), np.ascontiguousarray(g.tids, np.int64)]
         self._ck(self._L.hb_index_load(self._h, g.n, g.upper_rows, g.entry, _p(vecs), *[_p(a) for a in arrs]),
                  "hb_index_load")
+
+    def load_pgvector_pages(self, pages):
+        """pages: bytes / uint8 array holding the index relation's 8 kB blocks (metapage first)."""
+        buf = np.frombuffer(pages, np.uint8) if isinstance(pages, (bytes, bytearray)) else np.ascontiguousarray(pages, np.uint8)
+        if buf.size % 8192:
+            raise HnswError("index pages must be a multiple of 8192 bytes")
+        self._ck(self._L.hb_index_load_pgvector_pages(self._h, _p(buf), buf.size // 8192), "hb_index_load_pgvector_pages")
 
     def export_graph(self):
         n, m = self.n, self.m
