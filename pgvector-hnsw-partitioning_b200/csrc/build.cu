@@ -228,6 +228,20 @@ static __global__ void seg_heads_kernel(const unsigned long long *__restrict__ k
     if (e == 0 || (key[e - 1] >> LINK_KEY_SRC_BITS) != (k >> LINK_KEY_SRC_BITS)) seg_start[atomicAdd(nseg, 1)] = e;
 }
 
+// evaluated-distance logs -> hash tables (search_core.cuh EvalTable), one warp per new element
+static __global__ void eval_table_build_kernel(const uint32_t *__restrict__ el_id, const float *__restrict__ el_d,
+                                               const int32_t *__restrict__ el_n, int el_cap, int B, uint32_t *et_key,
+                                               float *et_val, int et_slots)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = (int) (((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (i >= B) return;
+    EvalTable et;
+    et.key = et_key + (size_t) i * et_slots; et.val = et_val + (size_t) i * et_slots; et.mask = (uint32_t) et_slots - 1u;
+    const int n = el_n[i];
+    for (int e = lane; e < n; e += 32) et.put(el_id[(size_t) i * el_cap + e], el_d[(size_t) i * el_cap + e], true);
+}
+
 // lists that this batch will shrink and whose pair cache is still unfilled: (layer << 32 | target)
 static __global__ void fill_list_kernel(const unsigned long long *__restrict__ key, const int32_t *__restrict__ seg_start,
                                         const int32_t *__restrict__ nseg, int m, const int32_t *__restrict__ nbr0,
@@ -347,6 +361,9 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
 
     // workspaces are sized once for the largest batch this call can form (cudaFree inside the
     // loop would stall the pipeline); a batch with unusually many upper-layer rows regrows them
+    // evaluated-distance table per new element: 32 x ef_construction slots (2048 at 64), 8 bytes each
+    int et_slots = 1;
+    while (et_slots < 32 * efc) et_slots <<= 1;
     auto size_workspaces = [&](int64_t b, int64_t UR1) -> int {
         hb::DevBuf *W = ix->ws_build;
         const int64_t E = b * m2 + UR1 * m;
@@ -358,6 +375,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         HB_CK(W[7].ensure(sizeof(int32_t) * b * DUP_SLOTS));
         HB_CK(W[8].ensure(sizeof(int32_t) * b * 2 + 64));                     // status | slow list
         HB_CK(W[9].ensure((size_t) E * (8 + 8 + 4 + 4 + 4 + 8) + 256));       // keys in/out | vals in/out | seg_start | fill list
+        if (ix->opt_eval_table) HB_CK(W[2].ensure((size_t) b * et_slots * 16 + (size_t) b * 4));   // evaluated-distance tables (keys | values) | logs (ids | distances) | counts
         HB_CK(ix->ws_misc.ensure(256));
         return HB_OK;
     };
@@ -585,6 +603,17 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         lp.dup = W[7].as<int32_t>();
         lp.totals = ix->d_totals;
         sp.fuse = ix->opt_fused_select;
+        uint32_t *et_key = nullptr;
+        float *et_val = nullptr;
+        if (ix->opt_eval_table) {
+            et_key = W[2].as<uint32_t>();
+            et_val = reinterpret_cast<float *>(et_key + (size_t) b * et_slots);
+            sp.el_id = reinterpret_cast<uint32_t *>(et_val + (size_t) b * et_slots);
+            sp.el_d = reinterpret_cast<float *>(sp.el_id + (size_t) b * et_slots);
+            sp.el_n = reinterpret_cast<int32_t *>(sp.el_d + (size_t) b * et_slots);
+            sp.el_cap = et_slots / 2;            // a table is at most half full
+            HB_CK(cudaMemsetAsync(et_key, 0xff, (size_t) b * et_slots * 4, s));
+        }
         sp.sel0_id = lp.sel0_id; sp.sel0_d = lp.sel0_d; sp.sel0_cnt = lp.sel0_cnt;
         sp.selu_id = lp.selu_id; sp.selu_d = lp.selu_d; sp.selu_cnt = lp.selu_cnt; sp.dup = lp.dup;
         HB_CK(HB_PICK(build_search, ix)(sp, ix->num_sms, slow_grid, s, false));
@@ -592,6 +621,11 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         sps.work = misc + 1; sps.qlist = sp.slow_list; sps.qcount = sp.slow_count;
         HB_CK(HB_PICK(build_search, ix)(sps, ix->num_sms, slow_grid, s, true));
 
+        if (et_key) {
+            eval_table_build_kernel<<<(int) ((b * 32 + 255) / 256), 256, 0, s>>>(sp.el_id, sp.el_d, sp.el_n, sp.el_cap, (int) b, et_key,
+                                                                                 et_val, et_slots);
+            HB_CK(cudaGetLastError());
+        }
         if (trace) cudaEventRecord(tev[1], s);
         if (!sp.fuse) HB_CK(HB_PICK(build_select, ix)(lp, ix->num_sms, s));
         build_check_kernel<<<(int) ((b + 255) / 256), 256, 0, s>>>(sp.status, lp.dup, (int) b, d_flag);
@@ -654,6 +688,8 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
             kp.nbr0 = ix->d_nbr0; kp.nbr0d = ix->d_nbr0d; kp.nbru = ix->d_nbru; kp.nbrud = ix->d_nbrud;
             kp.totals = ix->d_totals; kp.flag = d_flag;
             kp.pc0 = ix->d_pc0; kp.pv0 = ix->d_pv0; kp.pcu = ix->d_pcu; kp.pvu = ix->d_pvu;
+            // the tables are indexed by arrival order: usable only while ids = arrival order (no folded duplicates)
+            if (et_key && next == cur + b) { kp.et_key = et_key; kp.et_val = et_val; kp.et_slots = et_slots; }
             if (ix->d_pc0 && (ix->opt_link_kernel == 0 || ix->opt_link_kernel == 3) && ix->opt_pair_fill) {
                 // pair-cache fill pre-pass: triangles of the full, still unfilled lists this batch shrinks
                 fill_list_kernel<<<tgrid, 256, 0, s>>>(key_out, seg_start, d_nseg, m, ix->d_nbr0, ix->d_uoff, ix->d_nbru,
@@ -787,6 +823,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
 #ifdef HB_LINK_PROFILE
         unsigned long long t[16];
         cudaMemcpy(t, ix->d_totals, sizeof t, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[hb build] evaluated-distance tables: %llu lookups, %llu misses\n", t[14], t[15]);
         fprintf(stderr, "[hb build] link pipeline, warp-cycles: consumers total %.3g = wait %.3g + tiles %.3g + finalize %.3g (of which extra edges %.3g; %llu finalizes); producer total %.3g, waiting for a free stage %.3g; finalize parts: sort %.3g masks %.3g select %.3g\n",
                 (double) t[12], (double) t[6], (double) t[7], (double) t[8], (double) t[9], t[13], (double) t[11], (double) t[10],
                 (double) t[14], (double) t[15], (double) t[5]);

@@ -45,6 +45,8 @@ struct BuildSearchParams {
     int32_t *sel0_id; float *sel0_d; int32_t *sel0_cnt;     // B x 2m
     int32_t *selu_id; float *selu_d; int32_t *selu_cnt;     // UR x m
     int32_t *dup;                                           // B x DUP_SLOTS
+    // evaluated-distance logs (search_core.cuh EvalLog), B x el_cap entries each + B counts; NULL = not kept
+    uint32_t *el_id; float *el_d; int32_t *el_n; int el_cap;
 };
 
 template <typename T> __host__ __device__ inline size_t build_warp_smem(int nvec, int capW, int slots, bool slow)
@@ -130,9 +132,16 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_search_kernel(const Bu
         // 2nd phase: ef_construction candidates per layer; the whole result is the next entry list
         vs.configure(p.slots);
         int keep = 1;
+        EvalLog el;
+        el.id = p.el_id ? p.el_id + (size_t) i * p.el_cap : nullptr;
+        el.d = p.el_d ? p.el_d + (size_t) i * p.el_cap : nullptr;
+        el.n = 0; el.cap = p.el_cap;
         for (int lc = level; lc >= 0 && st == ST_OK; lc--) {
             wlist_as_entries(w, vs, keep, lane);
-            st = search_layer<T, IP, NV, G>(g, w, vs, q, p.efc, lc, lane, ctr);
+            if (el.id) {
+                NoDiscard nd;
+                st = search_layer<T, IP, NV, G, VS, NoDiscard, EvalLog>(g, w, vs, q, p.efc, lc, lane, ctr, nd, el);
+            } else st = search_layer<T, IP, NV, G>(g, w, vs, q, p.efc, lc, lane, ctr);
             if (st != ST_OK) break;
             keep = p.efc;
             const int cnt = min(w.L, p.efc);
@@ -195,6 +204,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32) build_search_kernel(const Bu
         }
         npair += np_e;
         if (lane == 0) {
+            if (p.el_n) p.el_n[i] = st == ST_OK ? min(el.n, el.cap) : 0;
             p.status[i] = st == ST_OK ? 0 : -st;
             atomicAdd(p.totals + 0, (unsigned long long) ctr.n_dist);
             atomicAdd(p.totals + 1, (unsigned long long) ctr.n_hop0);
@@ -545,26 +555,74 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32, 5) link_memo_kernel(const Li
                     }
                     have_matrix = true;
                 }
-                // the new elements against the members: every member row is fetched once
-                __syncwarp();
-                stage_row_nv<T, NV>(g.vecs + (size_t) srcA * g.row_bytes, g.nvec, q0, lane);
-                if (two) stage_row_nv<T, NV>(g.vecs + (size_t) srcB * g.row_bytes, g.nvec, q1, lane);
-                __syncwarp();
+                // the new elements against the members.  Their candidate searches expanded every neighbour
+                // they selected, so these distances were evaluated already and sit in the searches' tables
+                // (EvalTable); only what is missing there -- members that joined in this very batch, a
+                // crowded table -- is computed, each member row fetched once for both new elements.
+                EvalTable etA, etB;
+                const bool have_et = p.et_key != nullptr;
+                etA.key = etB.key = nullptr;
+                if (have_et) {
+                    etA.key = const_cast<uint32_t *>(p.et_key) + (size_t) (srcA - p.first) * p.et_slots;
+                    etA.val = const_cast<float *>(p.et_val) + (size_t) (srcA - p.first) * p.et_slots;
+                    etB.key = const_cast<uint32_t *>(p.et_key) + (size_t) (srcB - p.first) * p.et_slots;
+                    etB.val = const_cast<float *>(p.et_val) + (size_t) (srcB - p.first) * p.et_slots;
+                    etA.mask = etB.mask = (uint32_t) p.et_slots - 1u;
+                }
+                bool staged = false;
                 for (int jb = 0; jb < lm; jb += 32) {
                     const int j = jb + lane;
                     const int32_t nb = j < lm ? l_id[j] : -1;
-                    const unsigned msk = __ballot_sync(FULL, nb >= 0);
-                    if (two) {
-                        float vA, vB;
-                        eval_candidates2<T, IP, NV, (G > 2 ? 2 : G)>(g, q0, q1, nb, msk, lane, vA, vB);
-                        if (j < lm) { D[lm * ld + j] = vA; D[j * ld + lm] = vA; D2[j] = vB; }
-                    } else {
-                        const float vA = eval_candidates<T, IP, NV, G>(g, q0, nb, msk, lane);
-                        if (j < lm) { D[lm * ld + j] = vA; D[j * ld + lm] = vA; }
+                    float vA = 0.f, vB = 0.f;
+                    bool okA = false, okB = !two;
+                    if (have_et && nb >= 0) {
+                        okA = etA.get((uint32_t) nb, vA);
+                        if (two) okB = etB.get((uint32_t) nb, vB);
                     }
+                    const unsigned missA = __ballot_sync(FULL, nb >= 0 && !okA);
+                    const unsigned missB = __ballot_sync(FULL, nb >= 0 && !okB);
+#ifdef HB_LINK_PROFILE
+                    {
+                        const unsigned valid = __ballot_sync(FULL, nb >= 0);
+                        if (lane == 0) {
+                            atomicAdd(p.totals + 14, (unsigned long long) (__popc(valid) * (1 + two)));
+                            atomicAdd(p.totals + 15, (unsigned long long) (__popc(missA) + (two ? __popc(missB) : 0)));
+                        }
+                    }
+#endif
+                    if ((missA | missB) && !staged) {
+                        __syncwarp();
+                        stage_row_nv<T, NV>(g.vecs + (size_t) srcA * g.row_bytes, g.nvec, q0, lane);
+                        if (two) stage_row_nv<T, NV>(g.vecs + (size_t) srcB * g.row_bytes, g.nvec, q1, lane);
+                        __syncwarp();
+                        staged = true;
+                    }
+                    if (two && (missA & missB)) {
+                        float cA, cB;
+                        eval_candidates2<T, IP, NV, (G > 2 ? 2 : G)>(g, q0, q1, nb, missA & missB, lane, cA, cB);
+                        if ((missA & missB) >> lane & 1u) { vA = cA; vB = cB; }
+                    }
+                    const unsigned onlyA = two ? (missA & ~missB) : missA, onlyB = two ? (missB & ~missA) : 0u;
+                    if (onlyA) {
+                        const float c = eval_candidates<T, IP, NV, G>(g, q0, nb, onlyA, lane);
+                        if (onlyA >> lane & 1u) vA = c;
+                    }
+                    if (onlyB) {
+                        const float c = eval_candidates<T, IP, NV, G>(g, q1, nb, onlyB, lane);
+                        if (onlyB >> lane & 1u) vB = c;
+                    }
+                    if (j < lm) { D[lm * ld + j] = vA; D[j * ld + lm] = vA; if (two) D2[j] = vB; }
                 }
                 float dAB = 0.f;
-                if (two) dAB = staged_pair_distance<T, IP>(q0, q1, g.nvec, lane);
+                if (two) {
+                    if (!staged) {
+                        __syncwarp();
+                        stage_row_nv<T, NV>(g.vecs + (size_t) srcA * g.row_bytes, g.nvec, q0, lane);
+                        stage_row_nv<T, NV>(g.vecs + (size_t) srcB * g.row_bytes, g.nvec, q1, lane);
+                        __syncwarp();
+                    }
+                    dAB = staged_pair_distance<T, IP>(q0, q1, g.nvec, lane);
+                }
                 if (lane == 0) { l_id[lm] = srcA; l_d[lm] = dA; }
                 __syncwarp();
                 const int psA = link_select_slot(D, ld, l_id, l_d, ord, lm, lane, npair);

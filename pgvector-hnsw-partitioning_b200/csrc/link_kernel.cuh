@@ -55,6 +55,9 @@ struct LinkParams {
     // lists named here (key = layer << 32 | target; full lists whose triangle is not filled yet)
     const unsigned long long *fill_list;
     const int32_t *nfill;
+    // evaluated-distance tables of the batch's candidate searches (search_core.cuh EvalTable): table
+    // of new element first + i at et_key + i * et_slots.  NULL = not available (distances are computed)
+    const uint32_t *et_key; const float *et_val; int et_slots;
 };
 
 __device__ __forceinline__ uint32_t link_smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -271,7 +274,7 @@ __device__ __forceinline__ int link_select_slot(const float *D, int ld, const in
         const float v0 = D[si * ld + s0];
         const unsigned lo = __ballot_sync(FULL, lane < i && v0 <= di);
         unsigned hi = 0u;
-        if (nc > 32) {
+        if (nc > 33) {                     // position 32 can only fail candidates after it: none when nc = 33
             const float v1 = D[si * ld + s1];
             hi = __ballot_sync(FULL, lane + 32 < i && v1 <= di);
         }

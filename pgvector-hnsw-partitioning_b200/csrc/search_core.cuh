@@ -183,6 +183,60 @@ struct DiscList {            // unsorted list in HBM, one per query; n is warp-u
     }
 };
 
+// ---- evaluated distances (build) ----------------------------------------------------------------
+// The build keeps every query<->element distance its candidate search evaluates in a per-element
+// hash table in HBM: when the search of a layer ends, every member of W has been expanded, so the
+// new element already knows its distance to each neighbour of each neighbour it will link to --
+// exactly the distances HnswUpdateConnection asks for next (link_memo_kernel).  NoEvalSink
+// compiles to nothing.
+struct NoEvalSink {
+    static constexpr bool enabled = false;
+    __device__ __forceinline__ void put_mask(unsigned, uint32_t, float, int) {}
+};
+// what the search writes: an append-only log (two coalesced stores per batch of evaluations, nothing
+// to wait for); eval_table_build_kernel turns the logs into the hash tables afterwards
+struct EvalLog {
+    static constexpr bool enabled = true;
+    uint32_t *id;
+    float *d;
+    int n, cap;              // warp-uniform
+    __device__ __forceinline__ void put_mask(unsigned mask, uint32_t i, float dd, int lane)
+    {
+        const int pos = n + __popc(mask & ((1u << lane) - 1u));
+        if (((mask >> lane) & 1u) && pos < cap) { id[pos] = i; d[pos] = dd; }
+        n += __popc(mask);
+    }
+};
+struct EvalTable {           // open addressing, linear probing, at most EVAL_PROBES probes; EMPTY = free
+    static constexpr bool enabled = true;
+    static constexpr int EVAL_PROBES = 16;
+    uint32_t *key;
+    float *val;
+    uint32_t mask;           // slots - 1
+    __device__ __forceinline__ void put(uint32_t id, float d, bool active)
+    {
+        if (!active) return;
+        uint32_t h = (id * 0x9E3779B1u) >> 8 & mask;
+        for (int probe = 0; probe < EVAL_PROBES; probe++) {
+            const uint32_t old = atomicCAS(key + h, EMPTY, id);
+            if (old == EMPTY || old == id) { val[h] = d; return; }
+            h = (h + 1) & mask;
+        }
+        // table crowded: the reader computes this one again
+    }
+    __device__ __forceinline__ bool get(uint32_t id, float &d) const
+    {
+        uint32_t h = (id * 0x9E3779B1u) >> 8 & mask;
+        for (int probe = 0; probe < EVAL_PROBES; probe++) {
+            const uint32_t k = __ldcg(key + h);
+            if (k == id) { d = __ldcg(val + h); return true; }
+            if (k == EMPTY) return false;
+            h = (h + 1) & mask;
+        }
+        return false;
+    }
+};
+
 // ---- W list ---------------------------------------------------------------------------------
 // insert (ed, eid) keeping key order; then trim to ef + boundary ties.  `low` = every entry below
 // it is expanded.
@@ -333,9 +387,9 @@ __device__ __forceinline__ void eval_candidates2(const GraphView &g, const float
 
 // HnswSearchLayer.  Precondition: w holds the entry candidates (sorted, unexpanded) and vs holds
 // exactly their ids.  Postcondition: w[0 .. min(L, ef)) = the result, nearest first.
-template <typename T, int IP, int NV, int G, typename VS, typename DS>
+template <typename T, int IP, int NV, int G, typename VS, typename DS, typename ES>
 __device__ __forceinline__ int search_layer(const GraphView &g, WList &w, VS &vs, const float *q, int ef, int lc,
-                                            int lane, QueryCounters &ctr, DS &ds)
+                                            int lane, QueryCounters &ctr, DS &ds, ES &es)
 {
     const int deg = lc == 0 ? 2 * g.m : g.m;
     int low = 0;
@@ -368,6 +422,7 @@ __device__ __forceinline__ int search_layer(const GraphView &g, WList &w, VS &vs
             vs.added(__popc(nmask), sp);
             ctr.n_dist += __popc(nmask);
             const float myd = eval_candidates<T, IP, NV, G>(g, q, nb, nmask, lane);
+            if constexpr (ES::enabled) es.put_mask(nmask, (uint32_t) nb, myd, lane);
             const bool full = w.L >= ef;
             const float f = full ? w.d[ef - 1] : 0.f;
             unsigned amask = __ballot_sync(FULL, isnew && (!full || myd < f));
@@ -389,12 +444,20 @@ __device__ __forceinline__ int search_layer(const GraphView &g, WList &w, VS &vs
     return ST_OK;
 }
 
+template <typename T, int IP, int NV, int G, typename VS, typename DS>
+__device__ __forceinline__ int search_layer(const GraphView &g, WList &w, VS &vs, const float *q, int ef, int lc,
+                                            int lane, QueryCounters &ctr, DS &ds)
+{
+    NoEvalSink ne;
+    return search_layer<T, IP, NV, G, VS, DS, NoEvalSink>(g, w, vs, q, ef, lc, lane, ctr, ds, ne);
+}
 template <typename T, int IP, int NV, int G, typename VS>
 __device__ __forceinline__ int search_layer(const GraphView &g, WList &w, VS &vs, const float *q, int ef, int lc,
                                             int lane, QueryCounters &ctr)
 {
     NoDiscard nd;
-    return search_layer<T, IP, NV, G, VS, NoDiscard>(g, w, vs, q, ef, lc, lane, ctr, nd);
+    NoEvalSink ne;
+    return search_layer<T, IP, NV, G, VS, NoDiscard, NoEvalSink>(g, w, vs, q, ef, lc, lane, ctr, nd, ne);
 }
 
 // distance of the single element `e` (warp-uniform) to the staged query

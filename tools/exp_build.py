@@ -17,6 +17,9 @@ xh = (x.half() if half else x).cpu().numpy()
 ix = pkg.HnswIndex(dim, opc, 16, 64, capacity=n, seed=1)
 if batch:
     ix.set_option("build_batch", batch)
+for kv in os.environ.get("HB_OPTS", "").split(","):
+    if "=" in kv:
+        ix.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 if os.environ.get("LINK"):
     ix.set_option("link_kernel", int(os.environ["LINK"]))
 t0 = time.time(); ix.build(xh); dt = time.time() - t0
