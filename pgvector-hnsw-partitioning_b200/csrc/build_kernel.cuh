@@ -69,7 +69,7 @@ __device__ __forceinline__ int select_neighbors_warp(const GraphView &g, float *
                                                      unsigned long long &npair);
 
 template <typename T, int IP, int NV, int G, bool SLOW>
-__global__ void __launch_bounds__(BUILD_WARPS * 32) build_search_kernel(const BuildSearchParams p)
+__global__ void __launch_bounds__(BUILD_WARPS * 32, 4) build_search_kernel(const BuildSearchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
