@@ -81,6 +81,10 @@ int hb_index_entry(const hb_index *ix, int32_t *entry, int *entry_level);
  * skipped under HB_COSINE.  Returns the number of tuples indexed, or a negative error. */
 int64_t hb_build(hb_index *ix, const void *host_vecs, int64_t n, const int64_t *heap_tids);
 int64_t hb_insert(hb_index *ix, const void *host_vecs, int64_t n, const int64_t *heap_tids);
+/* Free the memory only inserts use (cached neighbour distances, the pair-distance cache -- 2 kB per
+ * element at m = 16 --, batch workspaces), as pgvector frees its in-memory build state when CREATE
+ * INDEX ends.  Scans are unaffected; a later hb_insert allocates what it needs again. */
+int hb_index_trim(hb_index *ix);
 /* largest batch of the GPU insert pipeline (0 = automatic: n/16, at most 8192, 16384 from 512k elements; 1 = the sequential
  * algorithm, graph identical to one-at-a-time insertion) */
 int hb_set_build_batch(hb_index *ix, int max_batch);

@@ -326,6 +326,21 @@ int hb_set_option(hb_index *ix, const char *name, int value)
     return HB_OK;
 }
 
+int hb_index_trim(hb_index *ix)
+{
+    if (!ix) return HB_EINVAL;
+    HB_CK(cudaSetDevice(ix->device));
+    HB_CK(cudaDeviceSynchronize());
+    // everything only inserts use: cached neighbour distances, the pair cache, batch workspaces.  A later
+    // hb_insert allocates them again (cached distances are recomputed, the pair cache refills lazily).
+    if (ix->d_nbr0d) { cudaFree(ix->d_nbr0d); ix->d_nbr0d = nullptr; }
+    if (ix->d_nbrud) { cudaFree(ix->d_nbrud); ix->d_nbrud = nullptr; }
+    hb::release_pair_cache(ix);
+    for (auto &b : ix->ws_build) b.release();
+    ix->ws_gbits.release(); ix->ws_gwd.release(); ix->ws_gwi.release(); ix->ws_ovf.release();
+    return HB_OK;
+}
+
 int hb_level_for(uint64_t seed, int64_t seq, int m) { return m >= 2 ? level_for(seed, seq, m) : HB_EINVAL; }
 
 int hb_set_build_batch(hb_index *ix, int max_batch) { return hb_set_option(ix, "build_batch", max_batch); }

@@ -452,6 +452,44 @@ template <typename T> __host__ __device__ inline size_t memo_warp_smem(int nvec,
 // per CTA: triangle index -> (a << 8 | b), so that a list's triangle moves with flat coalesced accesses
 __host__ __device__ inline size_t memo_lut_bytes(int lm0) { return ((size_t) lm0 * (lm0 - 1) / 2 * 2 + 15) & ~(size_t) 15; }
 
+// cold paths of link_memo_kernel, kept out of line so that its loop stays small in the instruction cache
+// first shrink of a list whose triangle the pre-pass did not fill: distances among its members
+template <typename T, int IP, int NV, int G>
+__device__ __noinline__ void memo_fill_matrix(const GraphView &g, float *q0, float *D, int ld, const int32_t *l_id, int lm, int lane)
+{
+    for (int a = 1; a < lm; a++) {
+        __syncwarp();
+        stage_row_nv<T, NV>(g.vecs + (size_t) l_id[a] * g.row_bytes, g.nvec, q0, lane);
+        __syncwarp();
+        for (int jb = 0; jb < a; jb += 32) {
+            const int j = jb + lane;
+            const int32_t nb = j < a ? l_id[j] : -1;
+            const float v = eval_candidates<T, IP, NV, G>(g, q0, nb, __ballot_sync(FULL, nb >= 0), lane);
+            if (j < a) { D[a * ld + j] = v; D[j * ld + a] = v; }
+        }
+    }
+}
+// distances the tables did not hold: new element A (and B) against the members flagged in missA / missB
+template <typename T, int IP, int NV, int G>
+__device__ __noinline__ void memo_eval_missing(const GraphView &g, const float *q0, const float *q1, int two, int32_t nb,
+                                               unsigned missA, unsigned missB, int lane, float &vA, float &vB)
+{
+    if (two && (missA & missB)) {
+        float cA, cB;
+        eval_candidates2<T, IP, NV, (G > 2 ? 2 : G)>(g, q0, q1, nb, missA & missB, lane, cA, cB);
+        if ((missA & missB) >> lane & 1u) { vA = cA; vB = cB; }
+    }
+    const unsigned onlyA = two ? (missA & ~missB) : missA, onlyB = two ? (missB & ~missA) : 0u;
+    if (onlyA) {
+        const float c = eval_candidates<T, IP, NV, G>(g, q0, nb, onlyA, lane);
+        if (onlyA >> lane & 1u) vA = c;
+    }
+    if (onlyB) {
+        const float c = eval_candidates<T, IP, NV, G>(g, q1, nb, onlyB, lane);
+        if (onlyB >> lane & 1u) vB = c;
+    }
+}
+
 template <typename T, int IP, int NV, int G>
 __global__ void __launch_bounds__(BUILD_WARPS * 32, 5) link_memo_kernel(const LinkParams p)
 {
@@ -540,18 +578,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32, 5) link_memo_kernel(const Li
                             D[a * ld + b] = v; D[b * ld + a] = v;
                         }
                     } else {
-                        // first shrink of this list: distances among its members
-                        for (int a = 1; a < lm; a++) {
-                            __syncwarp();
-                            stage_row_nv<T, NV>(g.vecs + (size_t) l_id[a] * g.row_bytes, g.nvec, q0, lane);
-                            __syncwarp();
-                            for (int jb = 0; jb < a; jb += 32) {
-                                const int j = jb + lane;
-                                const int32_t nb = j < a ? l_id[j] : -1;
-                                const float v = eval_candidates<T, IP, NV, G>(g, q0, nb, __ballot_sync(FULL, nb >= 0), lane);
-                                if (j < a) { D[a * ld + j] = v; D[j * ld + a] = v; }
-                            }
-                        }
+                        memo_fill_matrix<T, IP, NV, G>(g, q0, D, ld, l_id, lm, lane);
                     }
                     have_matrix = true;
                 }
@@ -597,20 +624,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32, 5) link_memo_kernel(const Li
                         __syncwarp();
                         staged = true;
                     }
-                    if (two && (missA & missB)) {
-                        float cA, cB;
-                        eval_candidates2<T, IP, NV, (G > 2 ? 2 : G)>(g, q0, q1, nb, missA & missB, lane, cA, cB);
-                        if ((missA & missB) >> lane & 1u) { vA = cA; vB = cB; }
-                    }
-                    const unsigned onlyA = two ? (missA & ~missB) : missA, onlyB = two ? (missB & ~missA) : 0u;
-                    if (onlyA) {
-                        const float c = eval_candidates<T, IP, NV, G>(g, q0, nb, onlyA, lane);
-                        if (onlyA >> lane & 1u) vA = c;
-                    }
-                    if (onlyB) {
-                        const float c = eval_candidates<T, IP, NV, G>(g, q1, nb, onlyB, lane);
-                        if (onlyB >> lane & 1u) vB = c;
-                    }
+                    if (missA | missB) memo_eval_missing<T, IP, NV, G>(g, q0, q1, two, nb, missA, missB, lane, vA, vB);
                     if (j < lm) { D[lm * ld + j] = vA; D[j * ld + lm] = vA; if (two) D2[j] = vB; }
                 }
                 float dAB = 0.f;

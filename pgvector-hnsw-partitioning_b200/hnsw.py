@@ -70,6 +70,7 @@ _SIGS = {
     "hb_build": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hb_insert": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hb_set_build_batch": (C.c_int, [C.c_void_p, C.c_int]),
+    "hb_index_trim": (C.c_int, [C.c_void_p]),
     "hb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "hb_level_for": (C.c_int, [C.c_uint64, C.c_int64, C.c_int]),
     "hb_index_load": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32] + [C.c_void_p] * 7),
@@ -218,6 +219,10 @@ class HnswIndex:
         vecs = self._vecs(vecs)
         t = None if heap_tids is None else np.ascontiguousarray(heap_tids, np.int64)
         return self._ck(self._L.hb_build(self._h, _p(vecs), vecs.shape[0], _p(t)), "hb_build")
+
+    def trim(self):
+        """free the build-only memory (pair cache, cached neighbour distances, workspaces)"""
+        self._ck(self._L.hb_index_trim(self._h), "hb_index_trim")
 
     def insert(self, vecs, heap_tids=None):
         """hnswinsert, batched."""

@@ -76,6 +76,22 @@ def test_insert_into_loaded_graph(oracle, pkg):
     ix.close()
 
 
+def test_trim_then_insert_again(oracle, pkg):
+    """hb_index_trim frees the build-only state; inserting afterwards rebuilds it and still matches the oracle."""
+    x = clustered(900, 20, 8, seed=13)
+    orc = oracle.Index(20, 8, 32, 0, 0, oracle.CANON, seed=2)
+    orc.build(x)
+    ix = pkg.HnswIndex(20, "vector_l2_ops", 8, 32, capacity=900, seed=2)
+    ix.set_option("build_batch", 1)
+    assert ix.build(x[:600]) == 600
+    ix.trim()
+    e, d, c = ix.search_elements(x[:5], 20)
+    assert (e[:, 0] == np.arange(5)).all()
+    assert ix.insert(x[600:], np.arange(600, 900)) == 300
+    graphs_equal(orc.export(), ix.export_graph())
+    ix.close()
+
+
 def recall(ids, gt):
     return float(np.mean([len(set(ids[i]) & set(gt[i])) / gt.shape[1] for i in range(len(gt))]))
 

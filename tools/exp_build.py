@@ -30,6 +30,6 @@ print("build %d x %d %s: %.2f s = %.0f vectors/s; n_dist %.0f/insert n_pair %.0f
 q = gen_set(1000, dim, 20260104 + 1000, dev)
 qh = (q.half() if half else q).cpu().numpy()
 gt, _, st = ix.bruteforce(qh, 10, stats=True)
-for ef in (40, 100):
+for ef in [int(v) for v in os.environ.get("EFS", "40,100").split(",")]:
     e, d, _ = ix.search_elements(qh, ef)
     print("  ef_search=%d recall@10=%.4f (exact scan: certified %d rescanned %d)" % (ef, recall_at(e[:, :10], gt), st["certified"], st["rescanned"]), flush=True)
