@@ -69,7 +69,7 @@ __device__ __forceinline__ int select_neighbors_warp(const GraphView &g, float *
                                                      unsigned long long &npair);
 
 template <typename T, int IP, int NV, int G, bool SLOW>
-__global__ void __launch_bounds__(BUILD_WARPS * 32, 4) build_search_kernel(const BuildSearchParams p)
+__global__ void __launch_bounds__(BUILD_WARPS * 32, (NV == 1 ? 6 : 4)) build_search_kernel(const BuildSearchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -452,10 +452,10 @@ template <typename T> __host__ __device__ inline size_t memo_warp_smem(int nvec,
 // per CTA: triangle index -> (a << 8 | b), so that a list's triangle moves with flat coalesced accesses
 __host__ __device__ inline size_t memo_lut_bytes(int lm0) { return ((size_t) lm0 * (lm0 - 1) / 2 * 2 + 15) & ~(size_t) 15; }
 
-// cold paths of link_memo_kernel, kept out of line so that its loop stays small in the instruction cache
+// the less travelled paths of link_memo_kernel (out of line they cost more in spills than they save in instruction cache: measured)
 // first shrink of a list whose triangle the pre-pass did not fill: distances among its members
 template <typename T, int IP, int NV, int G>
-__device__ __noinline__ void memo_fill_matrix(const GraphView &g, float *q0, float *D, int ld, const int32_t *l_id, int lm, int lane)
+__device__ __forceinline__ void memo_fill_matrix(const GraphView &g, float *q0, float *D, int ld, const int32_t *l_id, int lm, int lane)
 {
     for (int a = 1; a < lm; a++) {
         __syncwarp();
@@ -471,7 +471,7 @@ __device__ __noinline__ void memo_fill_matrix(const GraphView &g, float *q0, flo
 }
 // distances the tables did not hold: new element A (and B) against the members flagged in missA / missB
 template <typename T, int IP, int NV, int G>
-__device__ __noinline__ void memo_eval_missing(const GraphView &g, const float *q0, const float *q1, int two, int32_t nb,
+__device__ __forceinline__ void memo_eval_missing(const GraphView &g, const float *q0, const float *q1, int two, int32_t nb,
                                                unsigned missA, unsigned missB, int lane, float &vA, float &vB)
 {
     if (two && (missA & missB)) {
