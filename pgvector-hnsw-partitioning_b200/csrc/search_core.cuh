@@ -399,7 +399,17 @@ __device__ __forceinline__ int search_layer(const GraphView &g, WList &w, VS &vs
             const int i = base + lane;
             const bool un = i < w.L && !(w.id[i] & EXP_BIT);
             const unsigned b = __ballot_sync(FULL, un);
-            if (b) { idx = base + __ffs(b) - 1; break; }
+            if (b) {
+                idx = base + __ffs(b) - 1;
+                // the candidate after this one is the likeliest next expansion: start its neighbour list
+                // towards L2 now, a whole hop ahead of the load that will want it
+                const unsigned b2 = b & (b - 1);
+                if (lc == 0 && b2 && lane == 0) {
+                    const uint32_t nid = w.id[base + __ffs(b2) - 1] & ID_MASK;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(g.nbr0 + (size_t) nid * deg));
+                }
+                break;
+            }
         }
         if (idx < 0) break;
         const uint32_t cid = w.id[idx];
