@@ -110,6 +110,10 @@ int hb_index_load(hb_index *ix, int64_t n, int64_t upper_rows, int32_t entry, co
  * a cosine index are stored normalised already.  Deleted elements keep their place in the graph
  * and return no tuples. */
 int hb_index_load_pgvector_pages(hb_index *ix, const void *pages, int64_t n_pages);
+/* what the pages hold (metapage fields, element and upper-layer row counts) -- to size hb_index_create;
+ * host only, needs no device; any out pointer may be NULL */
+int hb_pgvector_pages_info(const void *pages, int64_t n_pages, int *dim, int *m, int *ef_construction,
+                           int64_t *n_elements, int64_t *upper_rows);
 int64_t hb_index_upper_rows(const hb_index *ix);
 /* any pointer may be NULL */
 int hb_index_export(const hb_index *ix, void *vecs, uint8_t *level, int32_t *nbr0, int32_t *uoff,

@@ -9,7 +9,7 @@ There is no CPU fallback: importing works anywhere (so the symbol table can be c
 compute call without the shared library or without a CUDA device raises.
 """
 from .hnsw import (  # noqa: F401
-    HB_COSINE, HB_F16, HB_F32, HB_HEAPTIDS, HB_IP, HB_L2, OPCLASSES, HnswError, HnswIndex, HnswScan,
-    build_library, lib_path, load_library, partition_of, partition_route, merge_topk_dev,
+    HB_COSINE, HB_F16, HB_F32, HB_HEAPTIDS, HB_IP, HB_L1, HB_L2, OPCLASSES, HnswError, HnswIndex, HnswIterator, HnswScan,
+    build_library, pgvector_pages_info, lib_path, load_library, partition_of, partition_route, merge_topk_dev,
 )
 from .partition import PartitionedIndex, exchange_topk, owned_partitions, split_rows  # noqa: F401

@@ -46,6 +46,35 @@ struct Elem { const uint8_t *tup; uint32_t blk; uint16_t off; };
 
 }   // namespace
 
+// metapage fields and tuple counts, so that the caller can size hb_index_create (no device needed)
+extern "C" int hb_pgvector_pages_info(const void *pages_v, int64_t n_pages, int *dim, int *m, int *ef_construction,
+                                      int64_t *n_elements, int64_t *upper_rows)
+{
+    using hb::set_error;
+    if (!pages_v || n_pages < 1) { set_error("hb_pgvector_pages_info: bad argument"); return HB_EINVAL; }
+    const uint8_t *pages = (const uint8_t *) pages_v;
+    const uint8_t *meta = pages + 24;
+    if (rd<uint32_t>(meta) != HNSW_MAGIC) { set_error("not a pgvector hnsw index: magic %08x", rd<uint32_t>(meta)); return HB_EINVAL; }
+    if (dim) *dim = (int) rd<uint32_t>(meta + 8);
+    if (m) *m = rd<uint16_t>(meta + 12);
+    if (ef_construction) *ef_construction = rd<uint16_t>(meta + 14);
+    int64_t ne = 0, ur = 0;
+    for (int64_t b = 1; b < n_pages; b++) {
+        const uint8_t *pg = pages + b * BLCKSZ;
+        const int lower = rd<uint16_t>(pg + 12);
+        if (lower < 24 || lower > BLCKSZ) { set_error("block %lld: corrupt page header", (long long) b); return HB_EINVAL; }
+        for (int i = 0; i < (lower - 24) / 4; i++) {
+            const uint32_t lp = rd<uint32_t>(pg + 24 + 4 * i);
+            const int off = lp & 0x7fff, flags = (lp >> 15) & 3, len = lp >> 17;
+            if (flags != 1 || len < 4 || off + len > BLCKSZ) continue;
+            if (pg[off] == 1) { ne++; ur += pg[off + 1]; }
+        }
+    }
+    if (n_elements) *n_elements = ne;
+    if (upper_rows) *upper_rows = ur;
+    return HB_OK;
+}
+
 extern "C" int hb_index_load_pgvector_pages(hb_index *ix, const void *pages_v, int64_t n_pages)
 {
     using hb::set_error;

@@ -76,6 +76,7 @@ _SIGS = {
     "hb_index_load": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32] + [C.c_void_p] * 7),
     "hb_index_upper_rows": (C.c_int64, [C.c_void_p]),
     "hb_index_load_pgvector_pages": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "hb_pgvector_pages_info": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 5),
     "hb_index_export": (C.c_int, [C.c_void_p] + [C.c_void_p] * 7),
     "hb_beginscan": (C.c_void_p, [C.c_void_p]),
     "hb_rescan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
@@ -421,6 +422,19 @@ class HnswScan:
             self._h = None
 
     __del__ = endscan
+
+
+def pgvector_pages_info(pages):
+    """(dim, m, ef_construction, n_elements, upper_rows) of a pgvector HNSW index relation's pages; host only."""
+    L = load_library()
+    buf = np.frombuffer(pages, np.uint8) if isinstance(pages, (bytes, bytearray)) else np.ascontiguousarray(pages, np.uint8)
+    if buf.size % 8192:
+        raise HnswError("index pages must be a multiple of 8192 bytes")
+    d, m, efc = C.c_int(), C.c_int(), C.c_int()
+    ne, ur = C.c_int64(), C.c_int64()
+    if L.hb_pgvector_pages_info(_p(buf), buf.size // 8192, C.byref(d), C.byref(m), C.byref(efc), C.byref(ne), C.byref(ur)) < 0:
+        raise _err(L, "hb_pgvector_pages_info")
+    return d.value, m.value, efc.value, ne.value, ur.value
 
 
 class HnswIterator:

@@ -62,3 +62,20 @@ def test_level_draw_matches_oracle(pkg, oracle):
     for m in (4, 16, 48):
         for i in range(3000):
             assert L.hb_level_for(99, i, m) == oracle.level_for(99, i, m)
+
+
+def test_pgvector_pages_info_on_cpu(pkg, oracle):
+    """host logic of the on-disk page reader that needs no device: metapage fields and tuple counts of pages
+    written in the recalled pgvector layout (tests/pgpages_writer.py)."""
+    import numpy as np
+    from conftest import clustered
+    from pgpages_writer import write_pages
+    x = clustered(500, 12, 8, seed=5)
+    orc = oracle.Index(12, 8, 32, 0, 0, oracle.CANON, seed=1)
+    orc.build(x, np.arange(500, dtype=np.int64) + 65537)
+    g = orc.export()
+    for scatter in (False, True):
+        blob = write_pages(g, 8, 32, 12, scatter=scatter)
+        assert pkg.pgvector_pages_info(blob) == (12, 8, 32, g.n, g.upper_rows)
+    with pytest.raises(pkg.HnswError):
+        pkg.pgvector_pages_info(b"\0" * 8192)
