@@ -561,7 +561,13 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         {
             int slots = 1; while (slots < efc * 16) slots <<= 1;
             if (slots < 1024) slots = 1024;
-            const size_t fixed = (size_t) ix->nvec * (ix->dtype == HB_F32 ? 4 : 8) * 4 + (size_t) sp.capW * 8 + 16;
+            const size_t fixed = (size_t) ix->nvec * (ix->dtype == HB_F32 ? 4 : 8) * 4 + (size_t) sp.capW * 8 + 16 +
+                                 (size_t) efc * 12 + (size_t) m2 * 8;
+            // twice the table while the CTAs the register budget allows (launch bounds of build_search_kernel)
+            // still fit shared memory: fewer searches spill into the overflow table in HBM
+            const int ctas = ix->nvec == 32 ? 6 : 4;
+            if (ix->opt_slots <= 0 && (fixed + (size_t) slots * 2 * 4) * BUILD_WARPS * ctas <= 216 * 1024) slots <<= 1;
+            if (ix->opt_slots > 0) { slots = 1; while (slots < ix->opt_slots) slots <<= 1; }
             while (slots > 256 && (fixed + (size_t) slots * 4) * BUILD_WARPS > 200 * 1024) slots >>= 1;
             sp.slots = slots;
             sp.upper_slots = std::min(slots, 1024);
