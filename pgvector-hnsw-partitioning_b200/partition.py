@@ -57,15 +57,22 @@ class PartitionedIndex:
 
     # ---- build: route rows to partitions, each rank indexes the partitions it owns; no collective
     def build(self, vecs, heap_tids=None):
+        """The partitions a rank owns are built concurrently (one host thread per partition: the handles
+        are independent and each has its own streams), so that the latency-bound small batches at the
+        start of every build overlap on the GPU."""
+        from concurrent.futures import ThreadPoolExecutor
         n = vecs.shape[0]
         tids = np.arange(n, dtype=np.int64) if heap_tids is None else np.ascontiguousarray(heap_tids, np.int64)
         rows = split_rows(tids, self.P, self.rank, self.world)
-        total = 0
-        for p, ix in self.parts.items():
+
+        def one(p):
             sel = rows[p]
-            if len(sel):
-                total += ix.insert(vecs[sel], tids[sel])
-        return total
+            return self.parts[p].insert(vecs[sel], tids[sel]) if len(sel) else 0
+
+        if len(self.parts) <= 1:
+            return sum(one(p) for p in self.parts)
+        with ThreadPoolExecutor(max_workers=min(len(self.parts), 8)) as ex:
+            return sum(ex.map(one, list(self.parts)))
 
     @property
     def n_local(self):
