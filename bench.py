@@ -173,6 +173,8 @@ def main():
 
     if args.impl == "reference" and rank != 0:
         return 0
+    # stdout carries the one JSON line and nothing else: NCCL's banner ("NCCL version ...") goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
     import torch
     import pgvector_hnsw_partitioning_b200 as pkg
