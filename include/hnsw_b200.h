@@ -94,7 +94,9 @@ int hb_level_for(uint64_t seed, int64_t seq, int m);
  * "per_query_counters" (0/1), "variant" (scan kernel tuning variant), "link_kernel" (reverse-link
  * kernel: 0 automatic, 1 warp per list, 2 pipelined TMA-staged, 3 memoised pair distances; all give
  * the same graph), "pair_cache" (0 = do not allocate the pair-distance cache), "pair_fill" (0 = fill
- * the cache in place instead of with the pre-pass).  0 restores the automatic choice. */
+ * the cache in place instead of with the pre-pass), "fused_select", "eval_table" (0 = the unfused /
+ * recomputing forms of the build kernels), "build_fraction" (a batch is at most 1/value of the graph,
+ * default 16).  0 restores the automatic choice. */
 int hb_set_option(hb_index *ix, const char *name, int value);
 
 /* ---- flat graph image (the layout in HBM; DESIGN.md "Data layout") ------------------------- */

@@ -322,6 +322,7 @@ int hb_set_option(hb_index *ix, const char *name, int value)
     else if (!strcmp(name, "pair_fill")) ix->opt_pair_fill = value;
     else if (!strcmp(name, "fused_select")) ix->opt_fused_select = value;
     else if (!strcmp(name, "eval_table")) ix->opt_eval_table = value;
+    else if (!strcmp(name, "build_fraction")) ix->opt_build_fraction = value > 0 ? value : 16;
     else { set_error("hb_set_option: unknown option %s", name); return HB_EINVAL; }
     return HB_OK;
 }

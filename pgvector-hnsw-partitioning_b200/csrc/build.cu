@@ -380,7 +380,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         return HB_OK;
     };
     {
-        const int64_t bmax = std::min<int64_t>(max_batch, std::max<int64_t>(1, std::min<int64_t>((int64_t) todo.size(), (ix->n + (int64_t) todo.size()) / 16)));
+        const int64_t bmax = std::min<int64_t>(max_batch, std::max<int64_t>(1, std::min<int64_t>((int64_t) todo.size(), (ix->n + (int64_t) todo.size()) / std::max(2, ix->opt_build_fraction))));
         rc = size_workspaces(bmax, std::max<int64_t>(bmax / 4, 64));
         if (rc) return rc;
         size_t sort_bytes = 0;
@@ -442,7 +442,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         const double t0 = now();
         n_batches++;
         const int64_t cur = ix->n;
-        int64_t b = std::max<int64_t>(1, std::min<int64_t>(auto_batch && cur < 524288 ? 8192 : max_batch, cur / 16));
+        int64_t b = std::max<int64_t>(1, std::min<int64_t>(auto_batch && cur < 524288 ? 8192 : max_batch, cur / std::max(2, ix->opt_build_fraction)));
         b = std::min<int64_t>(b, (int64_t) todo.size() - pos);
         levels.resize(b);
         for (int64_t i = 0; i < b; i++) levels[i] = (uint8_t) level_for(ix->seed, ix->seq + i, m);
@@ -715,7 +715,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         if (trace) cudaEventRecord(tev[4], s);
         HB_CK(cudaMemcpyAsync(ix->h_flag, d_flag, 12, cudaMemcpyDeviceToHost, s));
         // while the device works on this batch: the rows of the next one (at most ~cur/16 + a chunk ahead)
-        rc = upload_upto((int64_t) pos + b + std::min<int64_t>(max_batch, (cur + b) / 16 + 1));
+        rc = upload_upto((int64_t) pos + b + std::min<int64_t>(max_batch, (cur + b) / std::max(2, ix->opt_build_fraction) + 1));
         if (rc) return rc;
         const double t1 = now();
         HB_CK(cudaStreamSynchronize(s));
