@@ -2,17 +2,20 @@
 // UpdateGraphInMemory / UpdateNeighborsInMemory, hnswutils.c HnswFindElementNeighbors
 // [RECALL; reference mount empty, /root/reference/README.md:1]).
 //
-// Per batch, all on one stream with no host round trip in between:
-//   upload rows -> build_search_kernel (candidates per layer) -> build_select_kernel (heuristic
-//   selection + duplicate detection) -> build_check_kernel -> build_commit_kernel (AddConnections)
-//   -> edge_gen_kernel (reverse links as sortable keys) -> radix sort by (layer, target, source)
-//   -> seg_heads_kernel -> link kernel (HnswUpdateConnection, link_kernel.cuh).
+// Per batch, all on one stream with no host round trip in between (the rows of the NEXT batch are
+// uploaded meanwhile on a second stream):
+//   build_search_kernel (candidates per layer, SelectNeighbors fused in, duplicate detection; every
+//   distance it evaluates is logged) -> eval_table_build_kernel (logs -> per-element hash tables)
+//   -> build_check_kernel -> build_commit_kernel (AddConnections) -> edge_gen_kernel (reverse links as
+//   sortable keys) -> radix sort by (layer, target, source) -> seg_heads_kernel -> fill_list_kernel +
+//   link_pipe_kernel in fill mode (pair caches of lists shrunk for the first time) -> link_memo_kernel
+//   (HnswUpdateConnection; link_kernel.cuh, build_kernel.cuh).
 // The host assumes the batch holds no duplicate of an indexed vector (ids = arrival order) and
 // reads one flag word back per batch; when the check kernel found a duplicate the kernels after it
 // did nothing, the host folds the duplicates (FindDuplicateInMemory, <= 10 heap TIDs per element),
 // renumbers and re-runs the tail.  The host only moves bookkeeping integers; every distance is
-// evaluated on the GPU.  A batch is at most 1/16 of the current graph, and an element that would
-// raise the entry level is inserted alone.
+// evaluated on the GPU.  A batch is at most 1/16 of the current graph (8192, 16384 from 512k
+// elements), and an element that would raise the entry level is inserted alone.
 #include "index.h"
 #include "build_kernel.cuh"
 #include <cub/device/device_radix_sort.cuh>

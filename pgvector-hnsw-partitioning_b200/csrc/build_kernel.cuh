@@ -1,15 +1,16 @@
 // build_kernel.cuh -- the index-build hot path, batched.
 //
 // Roles [RECALL; the reference mount has no source, /root/reference/README.md:1]:
-//   build_search_kernel   <- hnswutils.c HnswFindElementNeighbors, search part: greedy descent then
-//                            HnswSearchLayer(ef_construction) per layer, for a whole batch of new
-//                            elements against the graph as it stood before the batch
-//   build_select_kernel   <- hnswutils.c SelectNeighbors + CheckElementCloser (heuristic with pruned
-//                            back-fill) and hnswbuild.c FindDuplicateInMemory
+//   build_search_kernel   <- hnswutils.c HnswFindElementNeighbors: greedy descent, then per layer
+//                            HnswSearchLayer(ef_construction) and -- fused, on the W just produced --
+//                            SelectNeighbors + CheckElementCloser (heuristic with pruned back-fill) and
+//                            hnswbuild.c FindDuplicateInMemory, for a whole batch of new elements against
+//                            the graph as it stood before the batch
+//   build_select_kernel   <- the selection as a kernel of its own (fused_select = 0)
 //   build_commit_kernel   <- hnswutils.c AddConnections (build.cu)
-//   link_pipe_kernel /    <- hnswutils.c HnswUpdateConnection (reverse links; re-selection when the
-//   link_warp_kernel         neighbour's list is full), one CTA or warp per (target, layer), edges
-//                            applied in source-id order (link_kernel.cuh)
+//   link_memo_kernel /    <- hnswutils.c HnswUpdateConnection (reverse links; re-selection when the
+//   link_pipe_kernel /       neighbour's list is full), one warp or CTA per (target, layer), edges
+//   link_warp_kernel         applied in source-id order (link_kernel.cuh describes the three)
 // A batch is what pgvector's parallel build workers are to each other: elements inserted
 // concurrently do not see one another.
 #pragma once
