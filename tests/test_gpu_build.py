@@ -142,3 +142,45 @@ def test_capacity_and_argument_errors(pkg):
     for bad in (dict(m=1), dict(m=101), dict(ef_construction=3), dict(m=40, ef_construction=64)):
         with pytest.raises(pkg.HnswError):
             pkg.HnswIndex(8, "vector_l2_ops", capacity=10, **bad)
+
+
+def test_large_m_uses_the_warp_link_kernel(oracle, pkg):
+    """2m > 63 candidates do not fit the 64-bit selection masks: the pair cache and the pipelined kernel are
+    bypassed and the warp-per-list kernel must still reproduce the oracle."""
+    n, dim, m = 700, 12, 36
+    x = clustered(n, dim, 8, seed=21)
+    orc = oracle.Index(dim, m, 2 * m, 0, 0, oracle.CANON, seed=4)
+    orc.build(x)
+    ix = pkg.HnswIndex(dim, "vector_l2_ops", m, 2 * m, capacity=n, seed=4)
+    ix.set_option("build_batch", 1)
+    assert ix.build(x) == n
+    graphs_equal(orc.export(), ix.export_graph())
+    ix.close()
+
+
+def test_batched_build_folds_duplicates(oracle, pkg):
+    """real batches + rows that duplicate vectors indexed by earlier batches: the flag path re-runs the tail
+    with folded numbering; every heap TID must stay reachable and the graph must stay a valid HNSW graph."""
+    n, dim = 6000, 24
+    x = clustered(n, dim, 16, seed=31)
+    x[3000:3040] = x[11]            # 40 copies of an early row: 10 TIDs per element, several elements
+    x[4000:4005] = x[2500]
+    x[5000] = x[4999]               # duplicate of a row of the same batch: may or may not fold
+    ix = pkg.HnswIndex(dim, "vector_l2_ops", 16, 64, capacity=n, seed=2)
+    assert ix.build(x) == n
+    g = ix.export_graph()
+    assert g.n < n and int(g.ntids.sum()) == n and g.ntids.max() == 10
+    all_tids = np.concatenate([g.tids[e, :g.ntids[e]] for e in range(g.n)])
+    assert sorted(all_tids.tolist()) == list(range(n))
+    assert ((g.nbr0 >= -1) & (g.nbr0 < g.n)).all() and not (g.nbr0 == np.arange(g.n)[:, None]).any()
+    t, d, c = ix.search(x[11:12], 60, 200)
+    want = set([11] + list(range(3000, 3040)))
+    assert want <= set(t[0, :c[0]].tolist()) and (d[0, :41] == 0).all()
+    # same rows, no duplicates: recall of the batched build with folds stays at the oracle's level
+    q = clustered(300, dim, 16, seed=32)
+    orc = oracle.Index.from_graph(g)
+    gt, _ = orc.bruteforce(q, 10, threads=8)
+    e, _, _ = ix.search_elements(q, 40)
+    rec = float(np.mean([len(set(e[i, :10]) & set(gt[i])) / 10 for i in range(len(q))]))
+    assert rec > 0.97, rec
+    ix.close()
