@@ -81,6 +81,10 @@ int hb_index_entry(const hb_index *ix, int32_t *entry, int *entry_level);
  * skipped under HB_COSINE.  Returns the number of tuples indexed, or a negative error. */
 int64_t hb_build(hb_index *ix, const void *host_vecs, int64_t n, const int64_t *heap_tids);
 int64_t hb_insert(hb_index *ix, const void *host_vecs, int64_t n, const int64_t *heap_tids);
+/* ambulkdelete, first pass (hnswvacuum.c RemoveHeapTids): the given heap TIDs leave the index; an
+ * element left without TIDs keeps routing searches and returns nothing.  Returns the number of TIDs
+ * removed.  The graph-repair passes of pgvector's vacuum are not implemented. */
+int64_t hb_bulk_delete(hb_index *ix, const int64_t *dead_tids, int64_t n_dead);
 /* Free the memory only inserts use (cached neighbour distances, the pair-distance cache -- 2 kB per
  * element at m = 16 --, batch workspaces), as pgvector frees its in-memory build state when CREATE
  * INDEX ends.  Scans are unaffected; a later hb_insert allocates what it needs again. */

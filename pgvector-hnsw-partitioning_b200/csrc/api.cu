@@ -373,6 +373,40 @@ static int sync_tids_to_device(hb_index *ix, int64_t first, int64_t n)
 }
 
 
+// ---- ambulkdelete, first pass -----------------------------------------------------------------
+// hnswvacuum.c RemoveHeapTids [RECALL]: dead heap TIDs leave their elements; an element left without TIDs
+// stays in the graph as a routing node and returns nothing.  Graph repair (RepairGraph / MarkDeleted: new
+// neighbours for elements that pointed at emptied ones, slot reuse) is not implemented.
+int64_t hb_bulk_delete(hb_index *ix, const int64_t *dead_tids, int64_t n_dead)
+{
+    if (!ix || (!dead_tids && n_dead > 0) || n_dead < 0) { set_error("hb_bulk_delete: bad argument"); return HB_EINVAL; }
+    if (n_dead == 0 || ix->n == 0) return 0;
+    HB_CK(cudaSetDevice(ix->device));
+    HB_CK(cudaDeviceSynchronize());
+    std::vector<int64_t> dead(dead_tids, dead_tids + n_dead);
+    std::sort(dead.begin(), dead.end());
+    int64_t removed = 0, lo = -1, hi = -1;
+    for (int64_t e = 0; e < ix->n; e++) {
+        int64_t *t = &ix->h_tids[(size_t) e * HB_HEAPTIDS];
+        const int nt = ix->h_ntids[e];
+        int w = 0;
+        for (int k = 0; k < nt; k++)
+            if (!std::binary_search(dead.begin(), dead.end(), t[k])) t[w++] = t[k];
+        if (w != nt) {
+            for (int k = w; k < HB_HEAPTIDS; k++) t[k] = 0;
+            ix->h_ntids[e] = (uint8_t) w;
+            removed += nt - w;
+            if (lo < 0) lo = e;
+            hi = e;
+        }
+    }
+    if (removed > 0) {
+        const int rc = sync_tids_to_device(ix, lo, hi - lo + 1);
+        if (rc) return rc;
+    }
+    return removed;
+}
+
 // ---- graph image ---------------------------------------------------------------------------
 int hb_index_load(hb_index *ix, int64_t n, int64_t upper_rows, int32_t entry, const void *vecs,
                   const uint8_t *level, const int32_t *nbr0, const int32_t *uoff, const int32_t *nbru,

@@ -817,6 +817,8 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
                 HB_CK(cudaMemcpy(ix->d_tidx + (size_t) c * (HB_HEAPTIDS - 1), &ix->h_tids[(size_t) c * HB_HEAPTIDS + 1],
                                  sizeof(int64_t) * (HB_HEAPTIDS - 1), cudaMemcpyHostToDevice));
                 HB_CK(cudaMemcpy(ix->d_ntids + c, &ix->h_ntids[c], 1, cudaMemcpyHostToDevice));
+                // slot 0 changes too when the element had been emptied by hb_bulk_delete
+                HB_CK(cudaMemcpy(ix->d_tid0 + c, &ix->h_tids[(size_t) c * HB_HEAPTIDS], sizeof(int64_t), cudaMemcpyHostToDevice));
             }
         }
         pos += b;

@@ -71,6 +71,7 @@ _SIGS = {
     "hb_insert": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hb_set_build_batch": (C.c_int, [C.c_void_p, C.c_int]),
     "hb_index_trim": (C.c_int, [C.c_void_p]),
+    "hb_bulk_delete": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
     "hb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "hb_level_for": (C.c_int, [C.c_uint64, C.c_int64, C.c_int]),
     "hb_index_load": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32] + [C.c_void_p] * 7),
@@ -220,6 +221,11 @@ class HnswIndex:
         vecs = self._vecs(vecs)
         t = None if heap_tids is None else np.ascontiguousarray(heap_tids, np.int64)
         return self._ck(self._L.hb_build(self._h, _p(vecs), vecs.shape[0], _p(t)), "hb_build")
+
+    def bulk_delete(self, dead_tids):
+        """ambulkdelete, first pass: remove heap TIDs; returns how many were removed"""
+        t = np.ascontiguousarray(dead_tids, np.int64)
+        return self._ck(self._L.hb_bulk_delete(self._h, _p(t), t.size), "hb_bulk_delete")
 
     def trim(self):
         """free the build-only memory (pair cache, cached neighbour distances, workspaces)"""

@@ -184,3 +184,39 @@ def test_batched_build_folds_duplicates(oracle, pkg):
     rec = float(np.mean([len(set(e[i, :10]) & set(gt[i])) / 10 for i in range(len(q))]))
     assert rec > 0.97, rec
     ix.close()
+
+
+def test_bulk_delete_removes_heap_tids(oracle, pkg):
+    """ambulkdelete first pass (RemoveHeapTids): dead TIDs are never returned again, elements left without
+    TIDs keep routing (results for the other rows unchanged apart from the dead ones dropping out), a later
+    insert of the same vector reuses the emptied element."""
+    n, dim = 3000, 20
+    x = clustered(n, dim, 16, seed=41)
+    x[1000:1004] = x[5]                                  # element of row 5 holds 5 TIDs
+    ix = pkg.HnswIndex(dim, "vector_l2_ops", 8, 32, capacity=n + 10, seed=3)
+    assert ix.build(x) == n
+    q = clustered(60, dim, 16, seed=42)
+    t0, d0, c0 = ix.search(q, 30, 100)
+    dead = np.array([5, 1001, 1003, 17, 18, 19, 2999, 123456789], np.int64)       # the last one is not in the index
+    assert ix.bulk_delete(dead) == 7
+    assert ix.bulk_delete(dead) == 0
+    t1, d1, c1 = ix.search(q, 30, 100)
+    deadset = set(dead.tolist())
+    for i in range(len(q)):
+        want = [t for t in t0[i, :c0[i]].tolist() if t not in deadset]
+        got = t1[i, :c1[i]].tolist()
+        assert not (set(got) & deadset)
+        assert got[:len(want)] == want and len(got) >= len(want)
+    t, d, c = ix.search(x[5:6], 10, 40)
+    assert sorted(t[0, :2].tolist()) == [1000, 1002] and d[0, 0] == 0 and d[0, 1] == 0 and d[0, 2] > 0
+    g = ix.export_graph()
+    assert int(g.ntids.sum()) == n - 7
+    e17 = int(np.nonzero((g.tids[:, 0] == 0) & (g.ntids == 0))[0][0])            # an emptied element is still in the graph
+    assert g.ntids[e17] == 0
+    # re-inserting a deleted vector folds into its emptied element (FindDuplicateInMemory)
+    before = ix.n
+    assert ix.insert(x[17:18], np.array([777777], np.int64)) == 1
+    assert ix.n == before
+    t, d, c = ix.search(x[17:18], 1, 40)
+    assert t[0, 0] == 777777 and d[0, 0] == 0
+    ix.close()
