@@ -645,11 +645,34 @@ int hb_search_batch_elements(hb_index *ix, const void *host_queries, int64_t nq,
     if (!wsp) { set_error("cannot create the scan workspace"); return HB_ECUDA; }
     ScanWs &ws = *wsp;
     cudaStream_t s = ws.own_stream;
-    HB_CK(ws.q.ensure((size_t) nq * ix->dim * ix->esize));
+    const size_t qbytes = (size_t) nq * ix->dim * ix->esize;
+    const size_t obytes = (size_t) nq * ef * 8 + (size_t) nq * 4;
+    HB_CK(ws.q.ensure(qbytes));
+    if (qbytes + obytes <= (256 << 10)) {
+        // small call (one backend's amgettuple): the caller's pageable buffers would make every copy a
+        // synchronous one; stage through pinned memory instead -- one H2D, one D2H, one synchronisation
+        if (!ws.h_pin) { HB_CK(cudaMallocHost(&ws.h_pin, 512 << 10)); ws.h_pin_cap = 512 << 10; }
+        HB_CK(ws.pack.ensure(obytes));
+        memcpy(ws.h_pin, host_queries, qbytes);
+        HB_CK(cudaMemcpyAsync(ws.q.p, ws.h_pin, qbytes, cudaMemcpyHostToDevice, s));
+        int32_t *d_elem = ws.pack.as<int32_t>();
+        float *d_dist = reinterpret_cast<float *>(d_elem + (size_t) nq * ef);
+        int32_t *d_cnt = reinterpret_cast<int32_t *>(d_dist + (size_t) nq * ef);
+        int rc = scan_dev(ix, ws, ws.q.p, nq, ef, d_elem, d_dist, d_cnt, s, nullptr, 0, 0);
+        if (rc) return rc;
+        char *h_out = ws.h_pin + qbytes;
+        HB_CK(cudaMemcpyAsync(h_out, ws.pack.p, obytes, cudaMemcpyDeviceToHost, s));
+        rc = check_status(ix, ws, nq, s);
+        if (rc) return rc;
+        memcpy(out_elem, h_out, (size_t) nq * ef * 4);
+        memcpy(out_dist, h_out + (size_t) nq * ef * 4, (size_t) nq * ef * 4);
+        if (out_cnt) memcpy(out_cnt, h_out + (size_t) nq * ef * 8, (size_t) nq * 4);
+        return HB_OK;
+    }
     HB_CK(ws.elem.ensure(sizeof(int32_t) * nq * ef));
     HB_CK(ws.dist.ensure(sizeof(float) * nq * ef));
     HB_CK(ws.cnt.ensure(sizeof(int32_t) * nq));
-    HB_CK(cudaMemcpyAsync(ws.q.p, host_queries, (size_t) nq * ix->dim * ix->esize, cudaMemcpyHostToDevice, s));
+    HB_CK(cudaMemcpyAsync(ws.q.p, host_queries, qbytes, cudaMemcpyHostToDevice, s));
     int rc = scan_dev(ix, ws, ws.q.p, nq, ef, ws.elem.as<int32_t>(), ws.dist.as<float>(), ws.cnt.as<int32_t>(), s, nullptr, 0, 0);
     if (rc) return rc;
     HB_CK(cudaMemcpyAsync(out_elem, ws.elem.p, sizeof(int32_t) * nq * ef, cudaMemcpyDeviceToHost, s));
@@ -725,6 +748,41 @@ int hb_search_batch_wait(hb_index *ix, int slot)
 int hb_search_batch(hb_index *ix, const void *host_queries, int64_t nq, int ef, int k, int64_t *out_tids,
                     float *out_dist, int32_t *out_cnt)
 {
+    if (!ix || !host_queries || !out_tids || !out_dist || k < 1) { set_error("hb_search_batch: bad argument"); return HB_EINVAL; }
+    const size_t qbytes = nq > 0 ? (size_t) nq * ix->dim * ix->esize : 0;
+    const size_t obytes = nq > 0 ? (size_t) nq * k * 12 + (size_t) nq * 4 : 0;
+    if (nq > 0 && qbytes + obytes <= (256 << 10)) {
+        // small call: stage through pinned memory (see hb_search_batch_elements) -- one H2D, one D2H, one wait
+        HB_CK(cudaSetDevice(ix->device));
+        ScanWs *wsp = ws_for_slot(ix, 0);
+        if (!wsp) { set_error("cannot create the scan workspace"); return HB_ECUDA; }
+        ScanWs &ws = *wsp;
+        if (ws.pending) { set_error("hb_search_batch: slot 0 still has a batch in flight"); return HB_ESTATE; }
+        cudaStream_t s = ws.own_stream;
+        if (!ws.h_pin) { HB_CK(cudaMallocHost(&ws.h_pin, 512 << 10)); ws.h_pin_cap = 512 << 10; }
+        HB_CK(ws.q.ensure(qbytes));
+        HB_CK(ws.elem.ensure(sizeof(int32_t) * nq * ef));
+        HB_CK(ws.dist.ensure(sizeof(float) * nq * ef));
+        HB_CK(ws.pack.ensure(obytes + 16));
+        memcpy(ws.h_pin, host_queries, qbytes);
+        HB_CK(cudaMemcpyAsync(ws.q.p, ws.h_pin, qbytes, cudaMemcpyHostToDevice, s));
+        int64_t *d_tids = ws.pack.as<int64_t>();
+        float *d_tdist = reinterpret_cast<float *>(d_tids + (size_t) nq * k);
+        int32_t *d_cnt = reinterpret_cast<int32_t *>(d_tdist + (size_t) nq * k);
+        int rc = scan_dev(ix, ws, ws.q.p, nq, ef, ws.elem.as<int32_t>(), ws.dist.as<float>(), d_cnt, s, nullptr, 0, 0);
+        if (rc) return rc;
+        elements_to_tids_kernel<<<(int) ((nq + 127) / 128), 128, 0, s>>>(ws.elem.as<int32_t>(), ws.dist.as<float>(), nq, ef, k,
+                                                                          ix->d_tid0, ix->d_ntids, ix->d_tidx, d_tids, d_tdist, d_cnt);
+        HB_CK(cudaGetLastError());
+        char *h_out = ws.h_pin + qbytes;
+        HB_CK(cudaMemcpyAsync(h_out, ws.pack.p, obytes, cudaMemcpyDeviceToHost, s));
+        rc = check_status(ix, ws, nq, s);
+        if (rc) return rc;
+        memcpy(out_tids, h_out, (size_t) nq * k * 8);
+        memcpy(out_dist, h_out + (size_t) nq * k * 8, (size_t) nq * k * 4);
+        if (out_cnt) memcpy(out_cnt, h_out + (size_t) nq * k * 12, (size_t) nq * 4);
+        return HB_OK;
+    }
     int rc = hb_search_batch_async(ix, 0, host_queries, nq, ef, k, out_tids, out_dist, out_cnt);
     if (rc) return rc;
     return hb_search_batch_wait(ix, 0);

@@ -47,9 +47,14 @@ struct ScanWs {
     int64_t pending_nq = 0;
     bool pending = false;
     int32_t *h_err = nullptr;               // pinned: error flag of the last batch
+    char *h_pin = nullptr;                  // pinned staging of small host-API calls (query in, results out)
+    size_t h_pin_cap = 0;
+    DevBuf pack;                            // small calls: elem | dist | cnt contiguous, one D2H
     void release()
     {
         if (h_err) cudaFreeHost(h_err);
+        if (h_pin) cudaFreeHost(h_pin);
+        pack.release();
         DevBuf *b[] = { &q, &qn, &elem, &dist, &cnt, &status, &slow, &misc, &pq, &tids, &tdist, &gbits, &gwd, &gwi, &ep, &ovf };
         for (auto x : b) x->release();
         if (ev0) cudaEventDestroy(ev0);

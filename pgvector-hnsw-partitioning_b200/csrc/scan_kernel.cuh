@@ -168,12 +168,23 @@ cudaError_t launch_scan_variant(const ScanParams &p, int num_sms, int max_grid, 
 {
     auto kern = scan_kernel<T, IP, NV, G, SLOW, MINB>;
     const size_t smem = scan_warp_smem<T>(p.g.nvec, p.capW, p.slots, SLOW) * SCAN_WARPS;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (e != cudaSuccess) return e;
+    // the function attribute and the occupancy query cost several microseconds each: remember them per
+    // device for the shared-memory size last used (a single scan is only ~350 us long)
+    static size_t seen_smem[16];
+    static int seen_bps[16];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 15;
     int bps = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SCAN_WARPS * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (bps < 1) return cudaErrorInvalidConfiguration;
+    if (seen_bps[dev] > 0 && seen_smem[dev] == smem) bps = seen_bps[dev];
+    else {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SCAN_WARPS * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (bps < 1) return cudaErrorInvalidConfiguration;
+        seen_smem[dev] = smem; seen_bps[dev] = bps;
+    }
     if (bps > MAX_CTAS_PER_SM) bps = MAX_CTAS_PER_SM;
     int64_t want = SLOW ? max_grid : (p.nq + SCAN_WARPS - 1) / SCAN_WARPS;
     int grid = (int) (want < (int64_t) bps * num_sms ? want : (int64_t) bps * num_sms);
