@@ -153,6 +153,13 @@ hb_iter *hb_iter_begin(hb_index *ix, const void *host_queries, int64_t nq, int e
 int64_t hb_iter_next(hb_iter *it, int32_t *elem, float *dist, int32_t *cnt);
 int hb_iter_tuples(hb_iter *it, int64_t *tuples /* nq: upstream's `tuples` counter */);
 void hb_iter_end(hb_iter *it);
+/* Filtered top-k on top of the resumable scans (what hnsw.iterative_scan is for): scans continue
+ * until k heap TIDs whose bit is set in allowed_bits (bit t = TID t, n_bits bits) were found, the
+ * index is exhausted or max_scan_tuples was reached.  relaxed_order.  out_tids/out_dist nq x k
+ * (-1 / +inf padded), out_cnt nq. */
+int hb_search_batch_filtered(hb_index *ix, const void *host_queries, int64_t nq, int ef_search, int k,
+                             const uint8_t *allowed_bits, int64_t n_bits, int64_t max_scan_tuples,
+                             int64_t *out_tids, float *out_dist, int32_t *out_cnt);
 
 /* ---- batched scan (the extension a GPU needs: many amrescan+amgettuple at once) ------------ */
 /* host buffers in, host buffers out; H2D and D2H copies happen inside.  For each of nq queries

@@ -4,6 +4,7 @@
 #include "index.h"
 #include "iter_kernel.cuh"
 
+#include <cmath>
 #include <vector>
 
 struct hb_iter {
@@ -141,6 +142,49 @@ int hb_iter_tuples(hb_iter *it, int64_t *tuples)
     HB_CK(cudaSetDevice(it->ix->device));
     HB_CK(cudaMemcpy(tuples, it->tuples.p, (size_t) it->nq * 8, cudaMemcpyDeviceToHost));
     return HB_OK;
+}
+
+// `ORDER BY col <op> $1 LIMIT k` under a WHERE clause the index cannot evaluate, the case
+// hnsw.iterative_scan exists for: scans are resumed until k tuples pass the filter (a bitmap over heap
+// TIDs: bit t set = tuple t qualifies), the index is exhausted or max_scan_tuples is reached.
+// relaxed_order semantics: tuples are kept in the order the scan produces them.
+int hb_search_batch_filtered(hb_index *ix, const void *host_queries, int64_t nq, int ef_search, int k,
+                             const uint8_t *allowed_bits, int64_t n_bits, int64_t max_scan_tuples, int64_t *out_tids,
+                             float *out_dist, int32_t *out_cnt)
+{
+    if (!ix || !host_queries || !allowed_bits || !out_tids || !out_dist || !out_cnt || k < 1 || nq < 1) {
+        set_error("hb_search_batch_filtered: bad argument");
+        return HB_EINVAL;
+    }
+    hb_iter *it = hb_iter_begin(ix, host_queries, nq, ef_search, max_scan_tuples);
+    if (!it) return HB_ECUDA;
+    std::vector<int32_t> elem((size_t) nq * ef_search), cnt(nq);
+    std::vector<float> dist((size_t) nq * ef_search);
+    for (int64_t i = 0; i < nq; i++) out_cnt[i] = 0;
+    for (int64_t i = 0; i < nq * k; i++) { out_tids[i] = -1; out_dist[i] = INFINITY; }
+    int rc = HB_OK;
+    for (;;) {
+        const int64_t got = hb_iter_next(it, elem.data(), dist.data(), cnt.data());
+        if (got < 0) { rc = (int) got; break; }
+        if (got == 0) break;
+        bool all_full = true;
+        for (int64_t q = 0; q < nq; q++) {
+            for (int j = 0; j < cnt[q] && out_cnt[q] < k; j++) {
+                const int32_t e = elem[(size_t) q * ef_search + j];
+                for (int t = ix->h_ntids[e] - 1; t >= 0 && out_cnt[q] < k; t--) {       // heaptids[--heaptidsLength]
+                    const int64_t tid = ix->h_tids[(size_t) e * HB_HEAPTIDS + t];
+                    if (tid < 0 || tid >= n_bits || !((allowed_bits[tid >> 3] >> (tid & 7)) & 1)) continue;
+                    out_tids[q * k + out_cnt[q]] = tid;
+                    out_dist[q * k + out_cnt[q]] = dist[(size_t) q * ef_search + j];
+                    out_cnt[q]++;
+                }
+            }
+            if (out_cnt[q] < k) all_full = false;
+        }
+        if (all_full) break;
+    }
+    hb_iter_end(it);
+    return rc;
 }
 
 void hb_iter_end(hb_iter *it)

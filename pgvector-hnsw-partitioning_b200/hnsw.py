@@ -88,6 +88,8 @@ _SIGS = {
     "hb_iter_next": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_iter_tuples": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hb_iter_end": (None, [C.c_void_p]),
+    "hb_search_batch_filtered": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_search_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_search_batch_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_search_batch_wait": (C.c_int, [C.c_void_p, C.c_int]),
@@ -276,6 +278,19 @@ class HnswIndex:
     # ---- scans
     def beginscan(self):
         return HnswScan(self)
+
+    def search_filtered(self, queries, k, ef_search, allowed, max_scan_tuples=20000):
+        """`ORDER BY ... LIMIT k` with a filter the index cannot evaluate: `allowed` is a boolean array over heap
+        TIDs (True = the tuple qualifies); scans are resumed (hnsw.iterative_scan) until k tuples pass."""
+        q = self._vecs(queries)
+        nq = q.shape[0]
+        bits = np.packbits(np.ascontiguousarray(allowed, bool), bitorder="little")
+        tids = np.empty((nq, k), np.int64)
+        dist = np.empty((nq, k), np.float32)
+        cnt = np.empty(nq, np.int32)
+        self._ck(self._L.hb_search_batch_filtered(self._h, _p(q), nq, ef_search, k, _p(bits), len(allowed), max_scan_tuples,
+                                                  _p(tids), _p(dist), _p(cnt)), "hb_search_batch_filtered")
+        return tids, dist, cnt
 
     def iterate(self, queries, ef_search=40, max_scan_tuples=20000):
         """hnsw.iterative_scan, batched: a resumable scan per query (see HnswIterator)."""

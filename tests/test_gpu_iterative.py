@@ -113,3 +113,26 @@ def test_rescan_resets_and_empty_index(pkg):
         assert sorted(got) == list(range(16)) and got[0] == 3
     sc.endscan()
     ix.close()
+
+
+def test_filtered_search_reaches_k(oracle, pkg):
+    """WHERE + ORDER BY + LIMIT: with a 5 % filter a plain ef_search=20 scan finds ~1 qualifying row; the
+    resumable scan keeps going until 10 are found, and they are the nearest qualifying rows the scan order yields."""
+    n, ef, k = 4000, 20, 10
+    x, q, orc, ix = make(oracle, pkg, 0, 0, 24, n)
+    rng = np.random.default_rng(0)
+    allowed = rng.random(n) < 0.05
+    t, d, c = ix.search_filtered(q, k, ef, allowed, max_scan_tuples=10 ** 9)
+    assert (c == k).all()
+    assert allowed[t].all()
+    for i in range(len(q)):
+        batches, _, _ = orc.iterate(q[i], ef, max_scan_tuples=10 ** 9)
+        stream = [int(e) for b in batches for e in b[0] if allowed[int(e)]]      # heap TID = element id here
+        assert list(t[i]) == stream[:k]
+    # the plain scan cannot satisfy the LIMIT
+    pt, pd, pc = ix.search(q, ef, ef)
+    assert np.mean([allowed[pt[i, :pc[i]]].sum() for i in range(len(q))]) < 3
+    # max_scan_tuples bounds the work: fewer than k may come back
+    t2, d2, c2 = ix.search_filtered(q, k, ef, np.zeros(n, bool), max_scan_tuples=500)
+    assert (c2 == 0).all()
+    ix.close()
