@@ -172,6 +172,10 @@ dist_launch_fn get_dist_launcher(int dtype, int kind)
 }
 
 constexpr int HB_OVERFLOW_SLOTS = 4096;
+static size_t scan_warp_smem_bytes(const hb_index *ix, int capW, int slots)
+{
+    return ix->dtype == HB_F32 ? scan_warp_smem<float>(ix->nvec, capW, slots, false) : scan_warp_smem<__half>(ix->nvec, capW, slots, false);
+}
 int normalize_dev(hb_index *ix, const void *dev_in, int64_t n, void *dev_out, cudaStream_t s)
 {
     const int wpb = 8;
@@ -593,8 +597,18 @@ static int scan_dev(hb_index *ix, ScanWs &ws, const void *dev_queries, int64_t n
 
     // per-warp visited overflow tables for the fast path (one slice per resident warp; the launcher
     // keeps at most MAX_CTAS_PER_SM CTAs per SM resident)
-    p.oslots = HB_OVERFLOW_SLOTS;
-    HB_CK(ws.ovf.ensure(sizeof(uint32_t) * (size_t) ix->num_sms * MAX_CTAS_PER_SM * SCAN_WARPS * p.oslots));
+    // Sized for the searches shared memory cannot hold: 64 slots per unit of ef_search (4096 .. 32768), so
+    // that data on which a scan visits thousands of elements (iid high-dimensional rows: ~36 evaluations
+    // per unit of ef) stays on the fast path instead of falling to the bitmap path.
+    {
+        int os = HB_OVERFLOW_SLOTS;
+        while (os < ef * 64 && os < 32768) os <<= 1;
+        p.oslots = os;
+        const size_t cta_smem = scan_warp_smem_bytes(ix, p.capW, p.slots) * SCAN_WARPS;
+        int ctas = (int) std::min<size_t>(MAX_CTAS_PER_SM, (227 * 1024) / std::max<size_t>(cta_smem, 1));
+        if (ctas < 1) ctas = 1;
+        HB_CK(ws.ovf.ensure(sizeof(uint32_t) * (size_t) ix->num_sms * ctas * SCAN_WARPS * p.oslots));
+    }
     p.ovf = ws.ovf.as<uint32_t>();
 
     const int ip = metric_kind(ix->metric);
