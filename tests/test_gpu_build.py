@@ -220,3 +220,23 @@ def test_bulk_delete_removes_heap_tids(oracle, pkg):
     t, d, c = ix.search(x[17:18], 1, 40)
     assert t[0, 0] == 777777 and d[0, 0] == 0
     ix.close()
+
+
+@pytest.mark.parametrize("dim", [1600, 2000])
+def test_wide_rows_single_stage_fill_and_in_place_fill(oracle, pkg, dim):
+    """6.4 kB rows leave room for ONE stage of the pipelined kernel (the pair-cache fill pre-pass runs unpipelined);
+    8 kB rows for none (the memoising kernel fills the matrix in place).  Both must reproduce the oracle."""
+    n = 900
+    x = clustered(n, dim, 8, seed=dim)
+    orc = oracle.Index(dim, 16, 64, 0, 0, oracle.CANON, seed=7)
+    orc.build(x)
+    ix = pkg.HnswIndex(dim, "vector_l2_ops", 16, 64, capacity=n, seed=7)
+    ix.set_option("build_batch", 1)
+    assert ix.build(x) == n
+    graphs_equal(orc.export(), ix.export_graph())
+    ix.close()
+    ix = pkg.HnswIndex(dim, "vector_l2_ops", 16, 64, capacity=n, seed=7)      # real batches: must terminate and search well
+    assert ix.build(x) == n
+    e, d, c = ix.search_elements(x[:50], 40)
+    assert (e[:, 0] == np.arange(50)).all()
+    ix.close()
