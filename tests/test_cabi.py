@@ -79,3 +79,21 @@ def test_pgvector_pages_info_on_cpu(pkg, oracle):
         assert pkg.pgvector_pages_info(blob) == (12, 8, 32, g.n, g.upper_rows)
     with pytest.raises(pkg.HnswError):
         pkg.pgvector_pages_info(b"\0" * 8192)
+
+
+def test_header_is_plain_c_and_links(pkg, tmp_path):
+    """include/hnsw_b200.h compiles as C99 -pedantic and every entry point it declares links against the .so
+    (tests/c/abi_smoke.c); its no-GPU error paths behave."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "tests", "c", "abi_smoke.c")).read()
+    missing = [n for n in declared_symbols() if "REF(%s)" % n not in src]
+    assert not missing, "tests/c/abi_smoke.c does not reference %s" % missing
+    so = pkg.lib_path()
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "c", "abi_smoke.c"), "-o", exe, so, "-Wl,-rpath," + os.path.dirname(so)])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "entry points" in out.stdout
