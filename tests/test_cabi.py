@@ -97,3 +97,17 @@ def test_header_is_plain_c_and_links(pkg, tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert "entry points" in out.stdout
+
+
+def test_c_example_builds(pkg, tmp_path):
+    """examples/knn.c (the ABI end to end from C) compiles and links; without a device it stops at the first call."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = pkg.lib_path()
+    exe = str(tmp_path / "knn")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "knn.c"),
+                           so, "-Wl,-rpath," + os.path.dirname(so), "-lm", "-o", exe])
+    if not has_gpu():
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 1 and "no CUDA device" in out.stderr
