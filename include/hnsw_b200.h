@@ -66,8 +66,9 @@ const char *hb_version(void);
 int hb_device_count(void);
 
 /* ---- index lifetime: hnswhandler reloptions (m, ef_construction) + opclass ---------------- */
-/* m in [2,100], ef_construction in [4,1000] and >= 2m (hnsw.c reloption checks).  capacity =
- * maximum number of elements; seed drives the level draw of HnswInitElement. */
+/* m in [2,100], ef_construction in [4,1000] and >= 2m (hnsw.c reloption checks).  capacity = number of
+ * elements to reserve room for (inserts beyond it grow the index, see hb_index_reserve); seed drives the
+ * level draw of HnswInitElement. */
 hb_index *hb_index_create(int device, int dim, int m, int ef_construction, int metric, int dtype,
                           int64_t capacity, uint64_t seed);
 void hb_index_free(hb_index *ix);
@@ -81,6 +82,9 @@ int hb_index_entry(const hb_index *ix, int32_t *entry, int *entry_level);
  * skipped under HB_COSINE.  Returns the number of tuples indexed, or a negative error. */
 int64_t hb_build(hb_index *ix, const void *host_vecs, int64_t n, const int64_t *heap_tids);
 int64_t hb_insert(hb_index *ix, const void *host_vecs, int64_t n, const int64_t *heap_tids);
+/* Grow the index to hold `capacity` elements (never shrinks).  hb_build / hb_insert call it themselves
+ * when rows arrive beyond the capacity (a pgvector index has none), unless the option "auto_grow" is 0. */
+int hb_index_reserve(hb_index *ix, int64_t capacity);
 /* ambulkdelete, first pass (hnswvacuum.c RemoveHeapTids): the given heap TIDs leave the index; an
  * element left without TIDs keeps routing searches and returns nothing.  Returns the number of TIDs
  * removed.  The graph-repair passes of pgvector's vacuum are not implemented. */

@@ -327,7 +327,58 @@ int hb_set_option(hb_index *ix, const char *name, int value)
     else if (!strcmp(name, "fused_select")) ix->opt_fused_select = value;
     else if (!strcmp(name, "eval_table")) ix->opt_eval_table = value;
     else if (!strcmp(name, "build_fraction")) ix->opt_build_fraction = value > 0 ? value : 16;
+    else if (!strcmp(name, "auto_grow")) ix->opt_auto_grow = value;
     else { set_error("hb_set_option: unknown option %s", name); return HB_EINVAL; }
+    return HB_OK;
+}
+
+// grow one device array: new allocation, fill pattern, old contents copied, old array freed
+extern "C++" {
+template <typename V> int grow_array(V *&p, size_t old_used, size_t new_count, int fill)
+{
+    if (!p) return HB_OK;
+    V *q = nullptr;
+    HB_CK(cudaMalloc(&q, sizeof(V) * new_count));
+    HB_CK(cudaMemset(q, fill, sizeof(V) * new_count));
+    if (old_used) HB_CK(cudaMemcpy(q, p, sizeof(V) * old_used, cudaMemcpyDeviceToDevice));
+    cudaFree(p);
+    p = q;
+    return HB_OK;
+}
+}   // extern "C++"
+
+int hb_index_reserve(hb_index *ix, int64_t capacity)
+{
+    if (!ix || capacity < 1 || capacity > 0x7ffffff0LL) { set_error("hb_index_reserve: bad argument"); return HB_EINVAL; }
+    if (capacity <= ix->cap) return HB_OK;
+    HB_CK(cudaSetDevice(ix->device));
+    HB_CK(cudaDeviceSynchronize());
+    const int m = ix->m, m2 = 2 * m;
+    const int64_t n = ix->n, ur = ix->upper_rows;
+    const int64_t ucap = std::max<int64_t>(ix->upper_cap, capacity / (m > 2 ? m - 1 : 1) + capacity / 16 + 1024);
+    const size_t tri0 = (size_t) m2 * (m2 - 1) / 2, triu = (size_t) m * (m - 1) / 2;
+    int rc;
+    {
+        char *q = nullptr;
+        HB_CK(cudaMalloc(&q, (size_t) capacity * ix->row_bytes));
+        if (n) HB_CK(cudaMemcpy(q, ix->d_vecs, (size_t) n * ix->row_bytes, cudaMemcpyDeviceToDevice));
+        cudaFree(ix->d_vecs);
+        ix->d_vecs = q;
+    }
+    if ((rc = grow_array(ix->d_nbr0, (size_t) n * m2, (size_t) capacity * m2, 0xff))) return rc;
+    if ((rc = grow_array(ix->d_uoff, (size_t) n, (size_t) capacity, 0xff))) return rc;
+    if ((rc = grow_array(ix->d_nbru, (size_t) ur * m, (size_t) ucap * m, 0xff))) return rc;
+    if ((rc = grow_array(ix->d_tid0, (size_t) n, (size_t) capacity, 0))) return rc;
+    if ((rc = grow_array(ix->d_ntids, (size_t) n, (size_t) capacity, 0))) return rc;
+    if ((rc = grow_array(ix->d_tidx, (size_t) n * (HB_HEAPTIDS - 1), (size_t) capacity * (HB_HEAPTIDS - 1), 0))) return rc;
+    if ((rc = grow_array(ix->d_nbr0d, (size_t) n * m2, (size_t) capacity * m2, 0))) return rc;
+    if ((rc = grow_array(ix->d_nbrud, (size_t) ur * m, (size_t) ucap * m, 0))) return rc;
+    if ((rc = grow_array(ix->d_pc0, (size_t) n * tri0, (size_t) capacity * tri0, 0))) return rc;
+    if ((rc = grow_array(ix->d_pcu, (size_t) ur * triu, (size_t) ucap * triu, 0))) return rc;
+    if ((rc = grow_array(ix->d_pv0, (size_t) n, (size_t) capacity, 0))) return rc;
+    if ((rc = grow_array(ix->d_pvu, (size_t) ur, (size_t) ucap, 0))) return rc;
+    ix->cap = capacity;
+    ix->upper_cap = ucap;
     return HB_OK;
 }
 

@@ -330,8 +330,14 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         todo.push_back(i);
     }
     if (ix->n + (int64_t) todo.size() > ix->cap) {
-        set_error("index capacity %lld exceeded (%lld + %lld)", (long long) ix->cap, (long long) ix->n, (long long) todo.size());
-        return HB_ENOMEM;
+        if (!ix->opt_auto_grow) {
+            set_error("index capacity %lld exceeded (%lld + %lld)", (long long) ix->cap, (long long) ix->n, (long long) todo.size());
+            return HB_ENOMEM;
+        }
+        // a pgvector index has no capacity: grow (at least by half, so that single-row inserts do not regrow every time)
+        const int64_t want = std::max<int64_t>(ix->n + (int64_t) todo.size(), ix->cap + ix->cap / 2 + 1024);
+        const int grc = hb_index_reserve(ix, want);
+        if (grc) return grc;
     }
     const double t_todo = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     int rc = ensure_build_arrays(ix, s);
@@ -467,7 +473,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         if (cur == 0) {
             // first element: becomes the entry point, no neighbours
             const int lv = levels[0];
-            if (lv > ix->upper_cap) { set_error("upper layer table full"); return HB_ENOMEM; }
+            if (lv > ix->upper_cap) { set_error("upper layer table full"); return HB_ENOMEM; }   // cannot happen: upper_cap >= 1024
             int32_t uo = lv > 0 ? 0 : -1;
             HB_CK(cudaMemcpyAsync(ix->d_uoff, &uo, sizeof uo, cudaMemcpyHostToDevice, s));
             HB_CK(cudaStreamSynchronize(s));
@@ -529,7 +535,17 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
             }
         }
         if (UR == 0) h_durow[0] = -1;
-        if (urows > ix->upper_cap) { set_error("upper layer table full (%lld rows)", (long long) urows); return HB_ENOMEM; }
+        if (urows > ix->upper_cap) {
+            // an unlucky run of level draws: more upper-layer rows than the n / (m - 1) expected ones
+            if (!ix->opt_auto_grow) { set_error("upper layer table full (%lld rows)", (long long) urows); return HB_ENOMEM; }
+            HB_CK(cudaStreamSynchronize(s));
+            HB_CK(cudaStreamSynchronize(up));
+            const int grc = hb_index_reserve(ix, ix->cap + ix->cap / 2 + 1024);
+            if (grc) return grc;
+            uploaded = (int64_t) pos;      // rows uploaded ahead lived in the old array: upload them again
+            slot_base = ix->n - uploaded;
+            continue;                      // form the batch again against the grown arrays
+        }
 
         hb::DevBuf *W = ix->ws_build;
         const int64_t E = (int64_t) b * m2 + (int64_t) UR * m;

@@ -71,6 +71,7 @@ _SIGS = {
     "hb_insert": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hb_set_build_batch": (C.c_int, [C.c_void_p, C.c_int]),
     "hb_index_trim": (C.c_int, [C.c_void_p]),
+    "hb_index_reserve": (C.c_int, [C.c_void_p, C.c_int64]),
     "hb_bulk_delete": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
     "hb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "hb_level_for": (C.c_int, [C.c_uint64, C.c_int64, C.c_int]),
@@ -228,6 +229,9 @@ class HnswIndex:
         """ambulkdelete, first pass: remove heap TIDs; returns how many were removed"""
         t = np.ascontiguousarray(dead_tids, np.int64)
         return self._ck(self._L.hb_bulk_delete(self._h, _p(t), t.size), "hb_bulk_delete")
+
+    def reserve(self, capacity):
+        self._ck(self._L.hb_index_reserve(self._h, capacity), "hb_index_reserve")
 
     def trim(self):
         """free the build-only memory (pair cache, cached neighbour distances, workspaces)"""

@@ -136,6 +136,7 @@ def test_build_is_deterministic(pkg):
 
 def test_capacity_and_argument_errors(pkg):
     ix = pkg.HnswIndex(8, "vector_l2_ops", 8, 32, capacity=10)
+    ix.set_option("auto_grow", 0)
     with pytest.raises(pkg.HnswError):
         ix.build(clustered(11, 8, 2, seed=1))
     ix.close()
@@ -239,4 +240,26 @@ def test_wide_rows_single_stage_fill_and_in_place_fill(oracle, pkg, dim):
     assert ix.build(x) == n
     e, d, c = ix.search_elements(x[:50], 40)
     assert (e[:, 0] == np.arange(50)).all()
+    ix.close()
+
+
+def test_index_grows_past_its_capacity(oracle, pkg):
+    """a pgvector index has no capacity: builds and inserts beyond the reservation grow the arrays (cached
+    distances and pair caches move along) and the graph stays the oracle's."""
+    n, dim = 2500, 16
+    x = clustered(n, dim, 8, seed=51)
+    orc = oracle.Index(dim, 8, 32, 0, 0, oracle.CANON, seed=9)
+    orc.build(x)
+    ix = pkg.HnswIndex(dim, "vector_l2_ops", 8, 32, capacity=64, seed=9)
+    ix.set_option("build_batch", 1)
+    assert ix.build(x[:1000]) == 1000                # 64 -> grows
+    for lo in range(1000, n, 300):                   # repeated hb_insert calls keep growing it
+        hi = min(n, lo + 300)
+        assert ix.insert(x[lo:hi], np.arange(lo, hi)) == hi - lo
+    graphs_equal(orc.export(), ix.export_graph())
+    ix.close()
+    ix = pkg.HnswIndex(dim, "vector_cosine_ops", 16, 64, capacity=100, seed=9)       # real batches, upload-ahead across a growth
+    assert ix.build(x) == n
+    e, d, c = ix.search_elements(x[:40], 40)
+    assert (e[:, 0] == np.arange(40)).all()
     ix.close()
