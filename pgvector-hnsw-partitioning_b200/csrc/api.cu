@@ -471,6 +471,14 @@ int hb_index_load(hb_index *ix, int64_t n, int64_t upper_rows, int32_t entry, co
         set_error("hb_index_load: NULL argument");
         return HB_EINVAL;
     }
+    if ((n > ix->cap || upper_rows > ix->upper_cap) && ix->opt_auto_grow) {
+        int64_t want = std::max<int64_t>(n, ix->cap);
+        const int mm = ix->m > 2 ? ix->m - 1 : 1;
+        while (want / mm + want / 16 + 1024 < upper_rows) want += want / 2 + 1024;     // upper_cap follows the capacity
+        if (want == ix->cap) want = ix->cap + 1;
+        const int grc = hb_index_reserve(ix, want);
+        if (grc) return grc;
+    }
     if (n > ix->cap || upper_rows > ix->upper_cap) {
         set_error("hb_index_load: graph (%lld elements, %lld upper rows) exceeds capacity", (long long) n, (long long) upper_rows);
         return HB_ENOMEM;

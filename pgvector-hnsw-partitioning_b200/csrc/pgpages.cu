@@ -113,7 +113,7 @@ extern "C" int hb_index_load_pgvector_pages(hb_index *ix, const void *pages_v, i
         }
     }
     const int64_t n = (int64_t) elems.size();
-    if (n > ix->cap) { set_error("index pages hold %lld elements, capacity is %lld", (long long) n, (long long) ix->cap); return HB_ENOMEM; }
+    if (n > ix->cap && !ix->opt_auto_grow) { set_error("index pages hold %lld elements, capacity is %lld", (long long) n, (long long) ix->cap); return HB_ENOMEM; }
     const int m2 = 2 * m;
     const size_t rowb = (size_t) ix->dim * ix->esize;
     std::vector<char> vecs((size_t) n * rowb);
@@ -137,7 +137,7 @@ extern "C" int hb_index_load_pgvector_pages(hb_index *ix, const void *pages_v, i
         memcpy(&vecs[(size_t) e * rowb], v + 8, rowb);
         if (level[e] > 0) { uoff[e] = (int32_t) urows; urows += level[e]; }
     }
-    if (urows > ix->upper_cap) { set_error("index pages hold %lld upper-layer rows, capacity is %lld", (long long) urows, (long long) ix->upper_cap); return HB_ENOMEM; }
+    if (urows > ix->upper_cap && !ix->opt_auto_grow) { set_error("index pages hold %lld upper-layer rows, capacity is %lld", (long long) urows, (long long) ix->upper_cap); return HB_ENOMEM; }
     nbru.assign((size_t) std::max<int64_t>(urows, 1) * m, -1);
     // pass 2: neighbour tuples
     for (int64_t e = 0; e < n; e++) {
