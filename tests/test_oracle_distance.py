@@ -98,3 +98,18 @@ def test_normalize_matches_float64(oracle):
     out, ok = O.normalize(h, O.F16)
     assert ok and out.dtype == np.float16
     assert abs(float((out.astype(np.float64) ** 2).sum()) - 1.0) < 5e-3
+
+
+@pytest.mark.parametrize("dim", [1, 3, 100, 128, 769, 1536])
+@pytest.mark.parametrize("dtype", [0, 1])
+def test_l1_vs_float64(oracle, dim, dtype):
+    """vector_l1_ops / halfvec_l1_ops FUNCTION 1 (pgvector 0.7 l1_distance): known answers [RECALL] and float64"""
+    O = oracle
+    assert O.distance([0, 0], [3, 4], O.L1) == 7.0 and O.distance([1, 2, 3], [3, 4, 5], O.L1) == 6.0
+    rng = np.random.default_rng(dim + 31 * dtype)
+    dt = np.float16 if dtype else np.float32
+    a, b = rng.standard_normal(dim).astype(dt), rng.standard_normal(dim).astype(dt)
+    ref = np.abs(a.astype(np.float64) - b.astype(np.float64)).sum()
+    for mode in (O.CANON, O.NATURAL):
+        assert abs(O.distance(a, b, O.L1, dtype, mode) - ref) <= 1e-5 * ref + 1e-30
+    assert O.distance(a, a, O.L1, dtype) == 0.0

@@ -157,3 +157,19 @@ def test_iterative_scan_properties(oracle):
         td = np.array([b[1][0] for b in capped[len(capped) - len(tail):]])
         assert (np.diff(td) >= 0).all()                  # leftovers in distance order
         assert sum(len(b[0]) for b in capped) == t2
+
+
+def test_l1_recall_vs_bruteforce(oracle):
+    O = oracle
+    x = clustered(4000, 32, 32, seed=21)
+    q = clustered(100, 32, 32, seed=22)
+    ix = O.Index(32, 16, 64, O.L1, O.F32, O.CANON, seed=3)
+    ix.build(x)
+    gt, gd = ix.bruteforce(q, 10, threads=4)
+    e, d, _, _ = ix.search_batch(q, 40, threads=4)
+    rec = np.mean([len(set(e[i, :10]) & set(gt[i])) / 10 for i in range(len(q))])
+    assert rec > 0.95, rec
+    # distances returned are l1 distances of the returned elements
+    i = 0
+    want = np.abs(x[e[i, 0]].astype(np.float64) - q[i].astype(np.float64)).sum()
+    assert abs(d[i, 0] - want) <= 1e-5 * want
