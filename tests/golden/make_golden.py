@@ -47,12 +47,38 @@ def make():
         out[name + "/uoff"] = g.uoff[:g.n]
         out[name + "/nbru"] = g.nbru[:g.upper_rows]
         out[name + "/ntids"] = g.ntids[:g.n]
-        out[name + "/tids"] = g.tids[:g.n]
+        t = g.tids[:g.n].copy()
+        t[np.arange(10)[None, :] >= g.ntids[:g.n, None]] = 0      # slots past ntids are not part of the fixture
+        out[name + "/tids"] = t
         out[name + "/res_elem"] = e
         out[name + "/res_dist"] = d
         out[name + "/res_cnt"] = c
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "hnsw_golden_v1.npz"), **out)
+    make_iter(out)
     return out
+
+
+def make_iter(base):
+    """resumable scans (hnsw.iterative_scan) and L1 on the "cos_f32" rows: the first batches of four queries with
+    and without a max_scan_tuples bound, and an L1 index's results -> hnsw_golden_iter_l1_v1.npz"""
+    x, q = base["cos_f32/x"], base["cos_f32/q"]
+    metric, dtype, dim, m, efc, seed, ef = (int(v) for v in base["cos_f32/params"])
+    out = {}
+    ix = O.Index(dim, m, efc, metric, dtype, O.CANON, seed=seed)
+    ix.build(x)
+    for qi in range(4):
+        for tag, mt in (("all", 10 ** 9), ("cap300", 300)):
+            batches, tuples, _ = ix.iterate(q[qi], 10, max_scan_tuples=mt, max_batches=12)
+            out["iter/%d/%s/elem" % (qi, tag)] = np.concatenate([b[0] for b in batches])
+            out["iter/%d/%s/dist" % (qi, tag)] = np.concatenate([b[1] for b in batches])
+            out["iter/%d/%s/sizes" % (qi, tag)] = np.array([len(b[0]) for b in batches], np.int32)
+    l1 = O.Index(dim, m, efc, O.L1, dtype, O.CANON, seed=seed)
+    l1.build(x)
+    g = l1.export()
+    e, d, c, _ = l1.search_batch(q, ef, threads=1)
+    out["l1/nbr0"] = g.nbr0[:g.n]
+    out["l1/res_elem"], out["l1/res_dist"] = e, d
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "hnsw_golden_iter_l1_v1.npz"), **out)
 
 
 if __name__ == "__main__":

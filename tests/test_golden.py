@@ -53,6 +53,27 @@ def test_golden_has_the_edge_cases():
     assert (d[:, 1:] == d[:, :-1]).any()  # exact distance ties in the result lists
 
 
+def test_oracle_reproduces_golden_resumable_scans_and_l1(oracle):
+    """hnsw_golden_iter_l1_v1.npz: the first batches of resumable scans (with and without max_scan_tuples) and
+    an L1 index on the cos_f32 rows"""
+    f = load("cos_f32")
+    z = np.load(os.path.join(os.path.dirname(GOLD), "hnsw_golden_iter_l1_v1.npz"))
+    metric, dtype, dim, m, efc, seed, ef = (int(v) for v in f["params"])
+    ix = oracle.Index(dim, m, efc, metric, dtype, oracle.CANON, seed=seed)
+    ix.build(f["x"])
+    for qi in range(4):
+        for tag, mt in (("all", 10 ** 9), ("cap300", 300)):
+            batches, _, _ = ix.iterate(f["q"][qi], 10, max_scan_tuples=mt, max_batches=12)
+            assert [len(b[0]) for b in batches] == z["iter/%d/%s/sizes" % (qi, tag)].tolist()
+            assert (np.concatenate([b[0] for b in batches]) == z["iter/%d/%s/elem" % (qi, tag)]).all()
+            assert (np.concatenate([b[1] for b in batches]).view(np.uint32) == z["iter/%d/%s/dist" % (qi, tag)].view(np.uint32)).all()
+    l1 = oracle.Index(dim, m, efc, oracle.L1, dtype, oracle.CANON, seed=seed)
+    l1.build(f["x"])
+    assert (l1.export().nbr0[:len(z["l1/nbr0"])] == z["l1/nbr0"]).all()
+    e, d, _, _ = l1.search_batch(f["q"], ef, threads=1)
+    assert (e == z["l1/res_elem"]).all() and (d.view(np.uint32) == z["l1/res_dist"].view(np.uint32)).all()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CASES)
 def test_cuda_scan_reproduces_golden(oracle, pkg, name):
