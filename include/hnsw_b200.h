@@ -46,7 +46,8 @@ enum {
 };
 
 #define HB_HEAPTIDS 10     /* HNSW_HEAPTIDS: duplicate heap TIDs kept per element */
-#define HB_MAX_DIM 16000   /* halfvec limit; vector is 2000 in pgvector's hnsw */
+#define HB_MAX_DIM 2000        /* HNSW_MAX_DIM: "column cannot have more than 2000 dimensions for hnsw index" (vector) */
+#define HB_MAX_DIM_HALF 4000   /* the same limit for halfvec (HNSW_MAX_DIM * 2) */
 #define HB_TIE_LIMIT 4096
 
 typedef struct hb_index hb_index;   /* one HNSW index = one partition, resident on one GPU  */
@@ -232,6 +233,48 @@ int hb_merge_topk_dev(int device, const int64_t *dev_tids, const float *dev_dist
 int hb_elements_to_tids_dev(hb_index *ix, const int32_t *dev_elem, const float *dev_dist,
                             int64_t nq, int ef, int k, int64_t *dev_out_tids, float *dev_out_dist,
                             void *stream);
+
+/* ---- the partitioned index (the fork's feature): P hash partitions over `world` GPUs -------------- */
+/* One process per GPU.  A row belongs to partition splitmix64(heap_tid) mod P; rank r owns the partitions
+ * {p : p mod world == r}, each an ordinary hb_index on the rank's GPU.  A search sends the same query batch
+ * to every partition, merges the owned partitions' top-k on the device, exchanges the per-rank lists with ONE
+ * ncclAllGather (12 bytes per result) and merges again: every rank ends with the same nq x k answer, ordered
+ * by (distance, heap TID).  The handle owns the NCCL communicator (NCCL is dlopen'ed when world > 1); all ranks
+ * must make the same sequence of hb_part_search_* calls, as in any NCCL program.  No CPU fallback. */
+typedef struct hb_part hb_part;
+#define HB_PART_ID_BYTES 128   /* sizeof(ncclUniqueId) */
+#define HB_PART_SLOTS 4        /* search batches that can be in flight */
+/* rank 0 obtains the communicator id and hands it to the other ranks by whatever means the host has
+ * (Postgres shared memory, a file, torch.distributed ...) */
+int hb_part_unique_id(void *id_out /* HB_PART_ID_BYTES */);
+/* collective when world > 1 (ncclCommInitRank); unique_id may be NULL when world == 1.  Partition p draws
+ * its levels from seed + p, whichever rank builds it. */
+hb_part *hb_part_create(int device, int dim, int m, int ef_construction, int metric, int dtype, int n_partitions,
+                        int64_t capacity_per_partition, uint64_t seed, int rank, int world, const void *unique_id);
+void hb_part_free(hb_part *pt);
+/* partitions this rank owns (ascending) -> count; partitions may be NULL */
+int hb_part_owned(const hb_part *pt, int32_t *partitions);
+/* the hb_index of an owned partition (owned by the hb_part; NULL when another rank owns it) */
+hb_index *hb_part_index(hb_part *pt, int partition);
+int64_t hb_part_size(const hb_part *pt);            /* elements over the owned partitions */
+int hb_part_set_option(hb_part *pt, const char *name, int value);   /* hb_set_option on every owned partition */
+int hb_part_get_counters(hb_part *pt, hb_counters *out, int reset); /* summed over the owned partitions */
+/* ambuild / aminsert: every rank passes the same tuples (or any superset of those it owns); each tuple is
+ * indexed by the owner of its partition, owned partitions are built concurrently, no collective.  Returns the
+ * number of tuples this rank indexed. */
+int64_t hb_part_build(hb_part *pt, const void *host_vecs, int64_t n, const int64_t *heap_tids);
+/* Batched ORDER BY ... LIMIT k over all partitions, asynchronous: queued on slot `slot` (0..HB_PART_SLOTS-1),
+ * completed by hb_part_search_wait.  root < 0: `queries` (nq x dim, index dtype) holds the batch on every
+ * rank already; root >= 0: only rank `root` passes queries and they are ncclBroadcast to the others first.
+ * queries_on_device / out_on_device: the buffers are device memory of this rank's GPU (ready when the call is
+ * made) instead of host memory (pinned for the copies to overlap).  out_tids / out_dist: nq x k, padded with
+ * -1 / +inf; every rank receives the full answer.  Buffers must stay valid until the wait. */
+int hb_part_search_async(hb_part *pt, int slot, const void *queries, int queries_on_device, int root, int64_t nq,
+                         int ef_search, int k, int64_t *out_tids, float *out_dist, int out_on_device);
+int hb_part_search_wait(hb_part *pt, int slot);
+/* synchronous, host buffers: slot 0 + wait */
+int hb_part_search(hb_part *pt, const void *host_queries, int root, int64_t nq, int ef_search, int k,
+                   int64_t *out_tids, float *out_dist);
 
 #ifdef __cplusplus
 }

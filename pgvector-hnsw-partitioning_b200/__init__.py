@@ -12,4 +12,4 @@ from .hnsw import (  # noqa: F401
     HB_COSINE, HB_F16, HB_F32, HB_HEAPTIDS, HB_IP, HB_L1, HB_L2, OPCLASSES, HnswError, HnswIndex, HnswIterator, HnswScan,
     build_library, pgvector_pages_info, lib_path, load_library, partition_of, partition_route, merge_topk_dev,
 )
-from .partition import PartitionedIndex, exchange_topk, owned_partitions, split_rows  # noqa: F401
+from .partition import PartitionedIndex, merge_rule, owned_partitions, share_unique_id, split_rows  # noqa: F401

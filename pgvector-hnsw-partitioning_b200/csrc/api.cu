@@ -254,7 +254,7 @@ static int index_alloc(hb_index *ix)
 hb_index *hb_index_create(int device, int dim, int m, int efc, int metric, int dtype, int64_t capacity,
                           uint64_t seed)
 {
-    if (dim < 1 || dim > HB_MAX_DIM || m < 2 || m > 100 || efc < 4 || efc > 1000 || efc < 2 * m ||
+    if (dim < 1 || dim > (dtype == HB_F16 ? HB_MAX_DIM_HALF : HB_MAX_DIM) || m < 2 || m > 100 || efc < 4 || efc > 1000 || efc < 2 * m ||
         metric < HB_L2 || metric > HB_L1 || (dtype != HB_F32 && dtype != HB_F16) || capacity < 1 ||
         capacity > 0x7ffffff0LL) {
         set_error("hb_index_create: invalid parameters (dim=%d m=%d ef_construction=%d metric=%d dtype=%d capacity=%lld)",
@@ -456,6 +456,7 @@ int64_t hb_bulk_delete(hb_index *ix, const int64_t *dead_tids, int64_t n_dead)
         }
     }
     if (removed > 0) {
+        ix->generation++;
         const int rc = sync_tids_to_device(ix, lo, hi - lo + 1);
         if (rc) return rc;
     }
@@ -491,6 +492,7 @@ int hb_index_load(hb_index *ix, int64_t n, int64_t upper_rows, int32_t entry, co
     if (upper_rows > 0)
         HB_CK(cudaMemcpy(ix->d_nbru, nbru, sizeof(int32_t) * upper_rows * ix->m, cudaMemcpyHostToDevice));
     ix->n = n; ix->seq = n; ix->upper_rows = upper_rows;
+    ix->generation++;
     ix->entry = n > 0 ? entry : -1;
     ix->entry_level = ix->entry >= 0 ? level[ix->entry] : -1;
     ix->h_level.assign(level, level + n);

@@ -479,30 +479,26 @@ static int make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t kpad, 
 struct BfState {
     DevBuf gthr, xb, xnh, misc, qraw, qn, qb, qnh, cand_score, cand_id, cand_thr, cand_dist, out_elem, out_dist, uncertain, iota, full_dist, dbg;
     int64_t built_n = -1;
+    uint64_t built_gen = 0;      // hb_index::generation the bf16 image was made from
     int kpad = 0;
 };
 
-static std::map<const hb_index *, BfState *> g_bf;
-
-static BfState *bf_state(const hb_index *ix)
+// the exact scan's state belongs to the handle (hb_index::bf): distinct handles share nothing
+static BfState *bf_state(hb_index *ix)
 {
-    auto it = g_bf.find(ix);
-    if (it != g_bf.end()) return it->second;
-    BfState *s = new BfState();
-    g_bf[ix] = s;
-    return s;
+    if (!ix->bf) ix->bf = new BfState();
+    return static_cast<BfState *>(ix->bf);
 }
 
-void bruteforce_release(const hb_index *ix)
+void bruteforce_release(hb_index *ix)
 {
-    auto it = g_bf.find(ix);
-    if (it == g_bf.end()) return;
-    BfState *s = it->second;
+    if (!ix->bf) return;
+    BfState *s = static_cast<BfState *>(ix->bf);
+    ix->bf = nullptr;
     DevBuf *b[] = { &s->gthr, &s->xb, &s->xnh, &s->misc, &s->qraw, &s->qn, &s->qb, &s->qnh, &s->cand_score, &s->cand_id, &s->cand_thr,
                     &s->cand_dist, &s->out_elem, &s->out_dist, &s->uncertain, &s->iota, &s->full_dist, &s->dbg };
     for (auto x : b) x->release();
     delete s;
-    g_bf.erase(it);
 }
 
 }   // namespace hb
@@ -536,8 +532,8 @@ int hb_bruteforce_ex(hb_index *ix, const void *host_queries, int64_t nq, int k, 
     HB_CK(st.misc.ensure(64));
     unsigned int *max_bits = st.misc.as<unsigned int>();
 
-    // bf16 image of the partition (rebuilt when the index grew)
-    if (st.built_n != n || st.kpad != kpad) {
+    // bf16 image of the partition (rebuilt whenever the index changed: every mutation bumps the generation)
+    if (st.built_n != n || st.kpad != kpad || st.built_gen != ix->generation) {
         HB_CK(st.xb.ensure((size_t) n * kpad * 2));
         HB_CK(st.xnh.ensure(sizeof(float) * n));
         HB_CK(cudaMemsetAsync(max_bits, 0, 4, s));
@@ -547,7 +543,7 @@ int hb_bruteforce_ex(hb_index *ix, const void *host_queries, int64_t nq, int k, 
         else
             to_bf16_kernel<__half><<<grid, wpb * 32, 0, s>>>(ix->d_vecs, ix->row_bytes, ix->dim, kpad, n, st.xb.as<__nv_bfloat16>(), st.xnh.as<float>(), max_bits);
         HB_CK(cudaGetLastError());
-        st.built_n = n; st.kpad = kpad;
+        st.built_n = n; st.kpad = kpad; st.built_gen = ix->generation;
     }
 
     // queries: H2D, normalise for cosine (exact path), bf16 copy padded to a whole tile

@@ -482,6 +482,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
             ix->h_tids.resize(HB_HEAPTIDS, 0);
             ix->h_tids[0] = tid_of(0);
             ix->upper_rows = lv; ix->n = 1; ix->entry = 0; ix->entry_level = lv; ix->seq += 1;
+            ix->generation++;
             // stale lists from a previous life of this slot
             HB_CK(cudaMemset(ix->d_nbr0, 0xff, sizeof(int32_t) * m2));
             if (lv > 0) HB_CK(cudaMemset(ix->d_nbru, 0xff, sizeof(int32_t) * (size_t) lv * m));
@@ -821,6 +822,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         }
         ix->n = next; ix->upper_rows = urows;
         ix->seq += b;
+        ix->generation++;
 
         // heap TIDs of elements that absorbed a duplicate
         if (!dirty.empty()) {

@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32, (NV == 1 ? 6 : 4)) build_sea
         // 1st phase: greedy search to the insert level
         vs.configure(p.upper_slots);
         for (int lc = g.entry_level; lc >= level + 1 && st == ST_OK; lc--) {
-            wlist_as_entries(w, vs, 1, lane);
-            st = search_layer<T, IP, NV, G>(g, w, vs, q, 1, lc, lane, ctr);
+            st = wlist_as_entries(w, vs, 1, lane);
+            if (st == ST_OK) st = search_layer<T, IP, NV, G>(g, w, vs, q, 1, lc, lane, ctr);
         }
         if (level > g.entry_level) level = g.entry_level;
         // 2nd phase: ef_construction candidates per layer; the whole result is the next entry list
@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32, (NV == 1 ? 6 : 4)) build_sea
         el.d = p.el_d ? p.el_d + (size_t) i * p.el_cap : nullptr;
         el.n = 0; el.cap = p.el_cap;
         for (int lc = level; lc >= 0 && st == ST_OK; lc--) {
-            wlist_as_entries(w, vs, keep, lane);
+            st = wlist_as_entries(w, vs, keep, lane);
+            if (st != ST_OK) break;
             if (el.id) {
                 NoDiscard nd;
                 st = search_layer<T, IP, NV, G, VS, NoDiscard, EvalLog>(g, w, vs, q, p.efc, lc, lane, ctr, nd, el);

@@ -76,6 +76,8 @@ struct hb_index {
     int32_t entry = -1;
     int entry_level = -1;
     bool has_dups = false;
+    uint64_t generation = 1;       // bumped by every mutation of the graph image (load, insert, delete, repair)
+    void *bf = nullptr;            // exact-scan state (bruteforce.cu BfState), owned by the handle
 
     // graph image in HBM
     char *d_vecs = nullptr;
@@ -162,7 +164,7 @@ inline int metric_kind(int metric) { return metric == HB_L2 ? 0 : (metric == HB_
 // api.cu: canonical l2_normalize of n rows resident in HBM
 int normalize_dev(hb_index *ix, const void *dev_in, int64_t n, void *dev_out, cudaStream_t s);
 // bruteforce.cu
-void bruteforce_release(const hb_index *ix);
+void bruteforce_release(hb_index *ix);
 // build.cu
 int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n, const int64_t *heap_tids);
 void release_pair_cache(hb_index *ix);

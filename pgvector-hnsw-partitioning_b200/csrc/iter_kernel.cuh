@@ -119,8 +119,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) iter_scan_kernel(const IterPa
                 w.L = 1;
                 __syncwarp();
                 for (int lc = g.entry_level; lc >= 1 && st == ST_OK; lc--) {
-                    wlist_as_entries(w, vh, 1, lane);
-                    st = search_layer<T, IP, NV, G>(g, w, vh, q, 1, lc, lane, ctr);
+                    st = wlist_as_entries(w, vh, 1, lane);
+                    if (st == ST_OK) st = search_layer<T, IP, NV, G>(g, w, vh, q, 1, lc, lane, ctr);
                 }
                 if (st == ST_OK) {
                     // layer 0 on the persistent bitmap (zeroed by the host); the entry point counts as a tuple

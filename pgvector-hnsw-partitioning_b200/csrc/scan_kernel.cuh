@@ -102,13 +102,13 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, MINB) scan_kernel(const ScanP
                 __syncwarp();
                 vs.configure(p.upper_slots);
                 for (int lc = g.entry_level; lc >= 1 && st == ST_OK; lc--) {
-                    wlist_as_entries(w, vs, 1, lane);
-                    st = search_layer<T, IP, NV, G>(g, w, vs, q, 1, lc, lane, ctr);
+                    st = wlist_as_entries(w, vs, 1, lane);
+                    if (st == ST_OK) st = search_layer<T, IP, NV, G>(g, w, vs, q, 1, lc, lane, ctr);
                 }
                 if (st == ST_OK) {
                     vs.configure(p.slots);
-                    wlist_as_entries(w, vs, 1, lane);
-                    st = search_layer<T, IP, NV, G>(g, w, vs, q, ef, 0, lane, ctr);
+                    st = wlist_as_entries(w, vs, 1, lane);
+                    if (st == ST_OK) st = search_layer<T, IP, NV, G>(g, w, vs, q, ef, 0, lane, ctr);
                 }
             }
         } else {
@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, MINB) scan_kernel(const ScanP
             }
             if (st == ST_OK) {
                 vs.configure(p.layer == 0 ? p.slots : p.upper_slots);
-                wlist_as_entries(w, vs, w.L, lane);
-                st = search_layer<T, IP, NV, G>(g, w, vs, q, ef, p.layer, lane, ctr);
+                st = wlist_as_entries(w, vs, w.L, lane);
+                if (st == ST_OK) st = search_layer<T, IP, NV, G>(g, w, vs, q, ef, p.layer, lane, ctr);
             }
         }
 
@@ -169,9 +169,10 @@ cudaError_t launch_scan_variant(const ScanParams &p, int num_sms, int max_grid, 
     auto kern = scan_kernel<T, IP, NV, G, SLOW, MINB>;
     const size_t smem = scan_warp_smem<T>(p.g.nvec, p.capW, p.slots, SLOW) * SCAN_WARPS;
     // the function attribute and the occupancy query cost several microseconds each: remember them per
-    // device for the shared-memory size last used (a single scan is only ~350 us long)
-    static size_t seen_smem[16];
-    static int seen_bps[16];
+    // device for the shared-memory size last used (a single scan is only ~350 us long); per host thread,
+    // so that handles driven from different threads never share mutable state
+    static thread_local size_t seen_smem[16];
+    static thread_local int seen_bps[16];
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 15;

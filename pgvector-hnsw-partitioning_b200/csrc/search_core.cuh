@@ -78,10 +78,11 @@ struct VisitedHash {         // shared-memory table + per-warp overflow table in
         }
         __syncwarp();
     }
-    // room for `incoming` more keys?  (warp-uniform)
+    // room for `incoming` more keys?  (warp-uniform; mirrors spill(): once a batch went to the overflow
+    // table every later one does, so from then on only the overflow table's load limit counts)
     __device__ __forceinline__ bool room(int incoming) const
     {
-        return count + incoming <= limit || ocount + incoming <= olimit;
+        return ocount > 0 ? ocount + incoming <= olimit : (count + incoming <= limit || incoming <= olimit);
     }
     // warp-uniform: where does this batch of `incoming` keys go
     // (sticky: once a batch spilled, every later batch of this layer search goes to the overflow
@@ -300,11 +301,14 @@ __device__ __forceinline__ int wlist_insert(WList &w, float ed, uint32_t eid, in
 
 // make the first min(L, keep) entries the entry list of the next HnswSearchLayer call: drop the
 // tie tail, clear expanded bits, reset the visited set and mark the entries visited.
+// Returns ST_TABLE when neither visited table can hold the entries (the caller hands the query to the
+// large-visited-set path).
 template <typename VS>
-__device__ __forceinline__ void wlist_as_entries(WList &w, VS &vs, int keep, int lane)
+__device__ __forceinline__ int wlist_as_entries(WList &w, VS &vs, int keep, int lane)
 {
     if (w.L > keep) w.L = keep;
     vs.clear(lane);
+    if (!vs.room(w.L)) return ST_TABLE;
     const bool sp = vs.spill(w.L);
     for (int base = 0; base < w.L; base += 32) {
         const int i = base + lane;
@@ -316,6 +320,7 @@ __device__ __forceinline__ void wlist_as_entries(WList &w, VS &vs, int keep, int
     }
     vs.added(w.L, sp);
     __syncwarp();
+    return ST_OK;
 }
 
 struct QueryCounters { int n_dist, n_hop0, n_hopu; };

@@ -109,6 +109,18 @@ _SIGS = {
     "hb_partition_route": (None, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "hb_merge_topk_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_elements_to_tids_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_part_unique_id": (C.c_int, [C.c_void_p]),
+    "hb_part_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_int, C.c_int, C.c_void_p]),
+    "hb_part_free": (None, [C.c_void_p]),
+    "hb_part_owned": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hb_part_index": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "hb_part_size": (C.c_int64, [C.c_void_p]),
+    "hb_part_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "hb_part_get_counters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "hb_part_build": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "hb_part_search_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "hb_part_search_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "hb_part_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 
@@ -183,9 +195,22 @@ class HnswIndex:
         if not self._h:
             raise _err(self._L, "hb_index_create")
 
+    @classmethod
+    def _view(cls, handle, dim, opclass, m, ef_construction, device, seed=0):
+        """A non-owning view of an hb_index that belongs to someone else (an hb_part's partition)."""
+        self = cls.__new__(cls)
+        self.metric, self.dtype = OPCLASSES[opclass]
+        self.opclass, self.dim, self.m, self.efc, self.device, self.seed = opclass, dim, m, ef_construction, device, seed
+        self.capacity = None
+        self._L = load_library()
+        self._h = handle
+        self._borrowed = True
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
-            self._L.hb_index_free(self._h)
+            if not getattr(self, "_borrowed", False):
+                self._L.hb_index_free(self._h)
             self._h = None
 
     __del__ = close

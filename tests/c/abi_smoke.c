@@ -19,6 +19,8 @@ int main(void)
     REF(hb_search_batch); REF(hb_search_batch_async); REF(hb_search_batch_wait); REF(hb_search_batch_elements); REF(hb_search_batch_dev);
     REF(hb_distance_batch); REF(hb_distance_batch_dev); REF(hb_normalize); REF(hb_bruteforce);
     REF(hb_partition_of); REF(hb_partition_route); REF(hb_merge_topk_dev); REF(hb_elements_to_tids_dev);
+    REF(hb_part_unique_id); REF(hb_part_create); REF(hb_part_free); REF(hb_part_owned); REF(hb_part_index); REF(hb_part_size);
+    REF(hb_part_set_option); REF(hb_part_get_counters); REF(hb_part_build); REF(hb_part_search_async); REF(hb_part_search_wait); REF(hb_part_search);
     REF(hb_get_counters); REF(hb_get_per_query_counters); REF(hb_last_search_ms); REF(hb_search_layer); REF(hb_bruteforce_ex);
 
     printf("version %s, %d entry points, %d device(s)\n", hb_version(), n_syms, hb_device_count());
@@ -34,6 +36,8 @@ int main(void)
         memset(page, 0, sizeof page);
         if (hb_pgvector_pages_info(page, 1, NULL, NULL, NULL, NULL, NULL) != HB_EINVAL) return 9;   /* wrong magic */
     }
+    if (hb_part_create(0, 8, 16, 64, HB_L2, HB_F32, 8, 10, 1, 1, 2, NULL) != NULL) return 12;   /* world 2 needs the communicator id */
+    if (hb_part_search_wait(NULL, 0) != HB_EINVAL) return 13;
     if (hb_device_count() <= 0) {
         /* no CUDA device: there is no CPU fallback, creation must fail and say why */
         if (hb_index_create(0, 8, 16, 64, HB_L2, HB_F32, 10, 1) != NULL) return 10;

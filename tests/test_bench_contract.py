@@ -48,3 +48,47 @@ def test_recall_helper():
     ids = np.array([[1, 2, 3, 4], [5, 6, 7, 8]])
     gt = np.array([[1, 2, 9, 10], [5, 6, 7, 8]])
     assert bench.recall_at(ids, gt) == 0.75
+
+
+def test_cpu_arm_child_process(tmp_path):
+    """oracle/cpu_arm.py (the process whose time bench.py reports as the CPU arm): loads a flat graph image,
+    times bounded steps, returns the ids both summation orders give; it imports neither torch nor the product."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import oracle as O
+    from conftest import clustered
+    src = open(os.path.join(ROOT, "oracle", "cpu_arm.py")).read()
+    assert "import torch" not in src and "pgvector_hnsw_partitioning_b200" not in src and "libhnsw_b200" not in src
+    x = clustered(3000, 32, 16, seed=4)
+    q = clustered(200, 32, 16, seed=5)
+    orc = O.Index(32, 16, 64, O.COSINE, O.F32, O.CANON, seed=3)
+    orc.build(x)
+    g = orc.export()
+    d = str(tmp_path)
+    for k in ("vecs", "level", "nbr0", "uoff", "nbru", "ntids", "tids"):
+        np.save(os.path.join(d, k + ".npy"), getattr(g, k))
+    json.dump({"dim": g.dim, "m": g.m, "efc": g.efc, "metric": g.metric, "dtype": g.dtype, "n": g.n, "upper_rows": g.upper_rows,
+               "entry": g.entry}, open(os.path.join(d, "meta.json"), "w"))
+    np.save(os.path.join(d, "queries.npy"), q)
+    np.save(os.path.join(d, "rows.npy"), x)
+    job = {"graph_dir": d, "queries": os.path.join(d, "queries.npy"), "ef": 40, "steps": 3, "warmup": 1, "budget_s": 1.0, "threads": 2,
+           "parity": 100, "parity_out": os.path.join(d, "parity.npz"),
+           "build": {"rows": os.path.join(d, "rows.npy"), "metric": 2, "dtype": 0, "n1": 500, "parts": 2, "n_part": 300}}
+    res = bench.run_cpu_child(job, d)
+    assert res["kind"] == "port" and res["queries_per_s"] > 0 and res["threads"] == 2 and 64 <= res["per_step"] <= 200
+    assert res["build"]["single_thread"]["vectors_per_s"] > 0 and res["build"]["concurrent"]["partitions"] == 2
+    par = dict(np.load(os.path.join(d, "parity.npz")))
+    oe, od, oc, octr = orc.search_batch(q[:100], 40, threads=2)
+    assert (par["canon_ids"] == oe).all() and (par["canon_dist"].view(np.uint32) == od.view(np.uint32)).all()
+    assert res["canon_counters"]["n_dist"] == octr["n_dist"]
+    # the parity record: identical ids -> everything identical; a perturbed id that is not a tie -> unexplained
+    rec = bench.parity_record(par, oe.copy(), od.copy())
+    assert rec["canonical_order"]["ids_identical"] == 100 and rec["canonical_order"]["distances_bit_identical"] == 100
+    nat = rec["natural_order_top10"]
+    assert nat["ids_identical"] + nat["within_1e-5_ties"] == 100 and nat["unexplained"] == 0
+    bad = oe.copy()
+    bad[0, 0] = oe[0, 20]
+    bd = od.copy()
+    bd[0, 0] = od[0, 20]
+    rec2 = bench.parity_record(par, bad, bd)
+    assert rec2["canonical_order"]["ids_identical"] == 99 and rec2["natural_order_top10"]["unexplained"] == 1

@@ -1,5 +1,7 @@
 """Host-side logic of the partitioned path with world_size 2 on CPU (gloo): routing, ownership,
-the all-gather exchange and the merge contract.  The kernels themselves are covered by -m gpu tests."""
+the shape of the one all-gather and the merge contract (ordered by (distance, tid), independent of how
+partitions are grouped into ranks).  The kernels and the NCCL path are covered by -m gpu tests
+(tests/test_gpu_partition.py, which spawns two NCCL ranks when two devices are visible)."""
 import os
 import socket
 
@@ -44,16 +46,20 @@ def _worker(rank, world, port, out):
     order = np.argsort(score[:, local_idx], axis=1, kind="stable")[:, :k]
     lt = torch.tensor(tids[local_idx][order])
     ld = torch.tensor(np.take_along_axis(score[:, local_idx], order, axis=1))
-    all_t, all_d = pkg.exchange_topk(lt, ld, world)
-    assert all_t.shape == (world, nq, k) and all_d.shape == (world, nq, k)
-    assert (all_t[rank] == lt).all()
-    # merge contract (hb_merge_topk_dev does this on the GPU): k best of the union, ties by rank
-    merged = []
-    for i in range(nq):
-        c = sorted((float(all_d[r, i, j]), r, int(all_t[r, i, j])) for r in range(world) for j in range(k))[:k]
-        merged.append([t for _, _, t in c])
+    # the one exchange of the data path: every rank's packed block [tids | dist], gathered (hb_part does this
+    # with ncclAllGather on the device; here gloo carries the same bytes)
+    block = torch.cat([lt.contiguous().view(torch.uint8).flatten(), ld.contiguous().view(torch.uint8).flatten()])
+    assert block.numel() == nq * k * 12
+    gathered = torch.empty(world * block.numel(), dtype=torch.uint8)
+    dist.all_gather_into_tensor(gathered, block)
+    blocks = gathered.view(world, -1)
+    all_t = [blocks[r, :nq * k * 8].view(torch.int64).view(nq, k).numpy() for r in range(world)]
+    all_d = [blocks[r, nq * k * 8:].view(torch.float32).view(nq, k).numpy() for r in range(world)]
+    assert (all_t[rank] == lt.numpy()).all()
+    # merge contract (part_merge_kernel): greedy head merge ordered by (distance, tid)
+    merged = np.array([pkg.merge_rule([(all_t[r][i], all_d[r][i]) for r in range(world)], k)[0] for i in range(nq)])
     want = tids[np.argsort(score, axis=1, kind="stable")[:, :k]]
-    assert (np.array(merged) == want).all()
+    assert (merged == want).all()
     out.put((rank, int(len(local_idx))))
     dist.destroy_process_group()
 
@@ -70,6 +76,34 @@ def test_partitioned_host_logic_world2():
         assert p.exitcode == 0
     got = dict(out.get() for _ in range(2))
     assert got[0] + got[1] == 4000
+
+
+def test_merge_rule_is_grouping_independent():
+    """Merging per rank and then across ranks equals one flat merge, exact ties included (the key
+    (distance, tid) is a total order): the answer does not depend on the world size."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import pgvector_hnsw_partitioning_b200 as pkg
+    rng = np.random.default_rng(9)
+    P, k = 8, 10
+    for trial in range(50):
+        lists = []
+        tid = rng.permutation(1000)
+        for p in range(P):
+            c = int(rng.integers(0, k + 1))
+            d = np.sort(rng.integers(0, 6, c)).astype(np.float32)          # few distinct values: many ties
+            t = np.full(k, -1, np.int64)
+            t[:c] = tid[p * k:p * k + c]                                    # within-list tie order is NOT by tid
+            dd = np.full(k, np.inf, np.float32)
+            dd[:c] = d
+            lists.append((t, dd))
+        flat = pkg.merge_rule(lists, k)
+        for world in (2, 4, 8):
+            per_rank = []
+            for r in range(world):
+                t, d = pkg.merge_rule([lists[p] for p in range(P) if p % world == r], k)
+                per_rank.append((np.array(t), np.array(d, np.float32)))
+            assert pkg.merge_rule(per_rank, k) == flat
 
 
 def test_owned_partitions_cover():
