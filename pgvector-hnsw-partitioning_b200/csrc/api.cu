@@ -5,6 +5,7 @@
 // no device is present.
 #include "index.h"
 #include "scan_kernel.cuh"
+#include "scan_reg.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -154,6 +155,7 @@ __global__ void merge_topk_kernel(const int64_t *__restrict__ tids, const float 
 #define HB_DECL(name)                                                                                         \
     cudaError_t scan_fast_##name(const ScanParams &, int, int, cudaStream_t, ScanLaunchInfo *);               \
     cudaError_t scan_slow_##name(const ScanParams &, int, int, cudaStream_t, ScanLaunchInfo *);               \
+    cudaError_t scan_reg_##name(const ScanParams &, int, int, int, cudaStream_t, ScanLaunchInfo *);           \
     cudaError_t dist_##name(const DistBatchParams &, cudaStream_t);
 HB_DECL(f32_l2) HB_DECL(f32_ip) HB_DECL(f16_l2) HB_DECL(f16_ip) HB_DECL(f32_l1) HB_DECL(f16_l1)
 #undef HB_DECL
@@ -164,6 +166,11 @@ scan_launch_fn get_scan_launcher(int dtype, int kind, bool slow)
         { { scan_fast_f32_l2, scan_slow_f32_l2 }, { scan_fast_f32_ip, scan_slow_f32_ip }, { scan_fast_f32_l1, scan_slow_f32_l1 } },
         { { scan_fast_f16_l2, scan_slow_f16_l2 }, { scan_fast_f16_ip, scan_slow_f16_ip }, { scan_fast_f16_l1, scan_slow_f16_l1 } } };
     return tab[dtype == HB_F32 ? 0 : 1][kind][slow ? 1 : 0];
+}
+scan_reg_launch_fn get_scan_reg_launcher(int dtype, int kind)
+{
+    static const scan_reg_launch_fn tab[2][3] = { { scan_reg_f32_l2, scan_reg_f32_ip, scan_reg_f32_l1 }, { scan_reg_f16_l2, scan_reg_f16_ip, scan_reg_f16_l1 } };
+    return tab[dtype == HB_F32 ? 0 : 1][kind];
 }
 dist_launch_fn get_dist_launcher(int dtype, int kind)
 {
@@ -665,7 +672,8 @@ static int scan_dev(hb_index *ix, ScanWs &ws, const void *dev_queries, int64_t n
         int os = HB_OVERFLOW_SLOTS;
         while (os < ef * 64 && os < 32768) os <<= 1;
         p.oslots = os;
-        const size_t cta_smem = scan_warp_smem_bytes(ix, p.capW, p.slots) * SCAN_WARPS;
+        // (the register-list kernel needs a little less shared memory per CTA than this: size for the smaller)
+        const size_t cta_smem = (scan_warp_smem_bytes(ix, p.capW, p.slots) - (size_t) p.capW * 8) * SCAN_WARPS;
         int ctas = (int) std::min<size_t>(MAX_CTAS_PER_SM, (227 * 1024) / std::max<size_t>(cta_smem, 1));
         if (ctas < 1) ctas = 1;
         HB_CK(ws.ovf.ensure(sizeof(uint32_t) * (size_t) ix->num_sms * ctas * SCAN_WARPS * p.oslots));
@@ -676,7 +684,9 @@ static int scan_dev(hb_index *ix, ScanWs &ws, const void *dev_queries, int64_t n
     HB_CK(cudaEventRecord(ws.ev0, s));
     p.work = misc + 0;
     ScanLaunchInfo info;
-    HB_CK(get_scan_launcher(ix->dtype, ip, false)(p, ix->num_sms, ix->opt_grid, s, &info));
+    const int regR = reg_list_R(ix->nvec, ef, dev_ep, ix->opt_variant);
+    if (regR) HB_CK(get_scan_reg_launcher(ix->dtype, ip)(p, regR, ix->num_sms, ix->opt_grid, s, &info));
+    else HB_CK(get_scan_launcher(ix->dtype, ip, false)(p, ix->num_sms, ix->opt_grid, s, &info));
     // queries whose tie tail (or overflow table) outgrew the fast path run again with a bitmap in HBM
     ScanParams ps = p;
     ps.work = misc + 1;

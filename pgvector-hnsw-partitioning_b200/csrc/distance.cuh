@@ -42,65 +42,71 @@ template <> struct Vec<__half> { static constexpr int VEC = 8; };
 // lane's 128-bit read is bank-conflict free: q[4*ch + k] (k<4) and q[plane + 4*ch + (k-4)].
 template <typename T> __device__ __forceinline__ int query_floats(int nvec) { return nvec * Vec<T>::VEC; }
 
+// ---- packed fp32 pairs --------------------------------------------------------------------------
+// sm_100 has two-wide fp32 instructions (PTX add/sub/fma.rn.f32x2 -> FADD2 / FFMA2): two independent IEEE
+// operations per issue slot, so results are bit-identical to the scalar forms.  Accumulators are kept as
+// pairs: pair p of a lane holds component slots 2p and 2p+1.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 pack2u(uint32_t lo, uint32_t hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 abs2(f32x2 a) { return a & 0x7fffffff7fffffffull; }
+
+template <int IP> __device__ __forceinline__ f32x2 accum_pair(f32x2 acc, f32x2 q, f32x2 v)
+{
+    if constexpr (IP == 1) return fma2(q, v, acc);
+    else if constexpr (IP == 2) return add2(acc, abs2(sub2(q, v)));
+    else {
+        const f32x2 t = sub2(q, v);
+        return fma2(t, t, acc);
+    }
+}
+
 // one 16-byte chunk of a row against the matching query components (already in registers)
 template <typename T, int IP>
-__device__ __forceinline__ void accum_chunk(float (&acc)[Vec<T>::VEC], const uint4 &raw, const float4 &qa,
+__device__ __forceinline__ void accum_chunk(f32x2 (&acc)[Vec<T>::VEC / 2], const uint4 &raw, const float4 &qa,
                                             const float4 &qb)
 {
     if constexpr (sizeof(T) == 4) {
-        const float v0 = __uint_as_float(raw.x), v1 = __uint_as_float(raw.y);
-        const float v2 = __uint_as_float(raw.z), v3 = __uint_as_float(raw.w);
-        if constexpr (IP == 1) {
-            acc[0] = fmaf(qa.x, v0, acc[0]);
-            acc[1] = fmaf(qa.y, v1, acc[1]);
-            acc[2] = fmaf(qa.z, v2, acc[2]);
-            acc[3] = fmaf(qa.w, v3, acc[3]);
-        } else if constexpr (IP == 2) {
-            acc[0] = acc[0] + fabsf(qa.x - v0);
-            acc[1] = acc[1] + fabsf(qa.y - v1);
-            acc[2] = acc[2] + fabsf(qa.z - v2);
-            acc[3] = acc[3] + fabsf(qa.w - v3);
-        } else {
-            float t;
-            t = qa.x - v0; acc[0] = fmaf(t, t, acc[0]);
-            t = qa.y - v1; acc[1] = fmaf(t, t, acc[1]);
-            t = qa.z - v2; acc[2] = fmaf(t, t, acc[2]);
-            t = qa.w - v3; acc[3] = fmaf(t, t, acc[3]);
-        }
+        acc[0] = accum_pair<IP>(acc[0], pack2(qa.x, qa.y), pack2u(raw.x, raw.y));
+        acc[1] = accum_pair<IP>(acc[1], pack2(qa.z, qa.w), pack2u(raw.z, raw.w));
     } else {
         const float2 h0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
         const float2 h1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
         const float2 h2 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.z));
         const float2 h3 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.w));
-        if constexpr (IP == 2) {
-            acc[0] = acc[0] + fabsf(qa.x - h0.x);
-            acc[1] = acc[1] + fabsf(qa.y - h0.y);
-            acc[2] = acc[2] + fabsf(qa.z - h1.x);
-            acc[3] = acc[3] + fabsf(qa.w - h1.y);
-            acc[4] = acc[4] + fabsf(qb.x - h2.x);
-            acc[5] = acc[5] + fabsf(qb.y - h2.y);
-            acc[6] = acc[6] + fabsf(qb.z - h3.x);
-            acc[7] = acc[7] + fabsf(qb.w - h3.y);
-        } else if constexpr (IP == 1) {
-            acc[0] = fmaf(qa.x, h0.x, acc[0]);
-            acc[1] = fmaf(qa.y, h0.y, acc[1]);
-            acc[2] = fmaf(qa.z, h1.x, acc[2]);
-            acc[3] = fmaf(qa.w, h1.y, acc[3]);
-            acc[4] = fmaf(qb.x, h2.x, acc[4]);
-            acc[5] = fmaf(qb.y, h2.y, acc[5]);
-            acc[6] = fmaf(qb.z, h3.x, acc[6]);
-            acc[7] = fmaf(qb.w, h3.y, acc[7]);
-        } else {
-            float t;
-            t = qa.x - h0.x; acc[0] = fmaf(t, t, acc[0]);
-            t = qa.y - h0.y; acc[1] = fmaf(t, t, acc[1]);
-            t = qa.z - h1.x; acc[2] = fmaf(t, t, acc[2]);
-            t = qa.w - h1.y; acc[3] = fmaf(t, t, acc[3]);
-            t = qb.x - h2.x; acc[4] = fmaf(t, t, acc[4]);
-            t = qb.y - h2.y; acc[5] = fmaf(t, t, acc[5]);
-            t = qb.z - h3.x; acc[6] = fmaf(t, t, acc[6]);
-            t = qb.w - h3.y; acc[7] = fmaf(t, t, acc[7]);
-        }
+        acc[0] = accum_pair<IP>(acc[0], pack2(qa.x, qa.y), pack2(h0.x, h0.y));
+        acc[1] = accum_pair<IP>(acc[1], pack2(qa.z, qa.w), pack2(h1.x, h1.y));
+        acc[2] = accum_pair<IP>(acc[2], pack2(qb.x, qb.y), pack2(h2.x, h2.y));
+        acc[3] = accum_pair<IP>(acc[3], pack2(qb.z, qb.w), pack2(h3.x, h3.y));
     }
 }
 
@@ -108,6 +114,14 @@ template <int VEC> __device__ __forceinline__ float fold_lane(const float (&a)[V
 {
     if constexpr (VEC == 4) return (a[0] + a[1]) + (a[2] + a[3]);
     else return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+}
+// the same fold over packed accumulators
+template <int VEC> __device__ __forceinline__ float fold_lane2(const f32x2 (&p)[VEC / 2])
+{
+    float a[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC / 2; k++) unpack2(p[k], a[2 * k], a[2 * k + 1]);
+    return fold_lane<VEC>(a);
 }
 
 // Lane partials of G candidate rows against the query in shared memory.
@@ -121,11 +135,11 @@ __device__ __forceinline__ void group_partials(const char *__restrict__ vecs, ui
 {
     constexpr int VEC = Vec<T>::VEC;
     constexpr bool HALF = sizeof(T) == 2;
-    float acc[G][VEC];
+    f32x2 acc[G][VEC / 2];
 #pragma unroll
     for (int c = 0; c < G; c++)
 #pragma unroll
-        for (int k = 0; k < VEC; k++) acc[c][k] = 0.0f;
+        for (int k = 0; k < VEC / 2; k++) acc[c][k] = 0ull;
     const char *rp[G];
 #pragma unroll
     for (int c = 0; c < G; c++) rp[c] = vecs + (uint64_t) (uint32_t) ids[c] * row_bytes + 16 * lane;
@@ -159,7 +173,7 @@ __device__ __forceinline__ void group_partials(const char *__restrict__ vecs, ui
         }
     }
 #pragma unroll
-    for (int c = 0; c < G; c++) part[c] = fold_lane<VEC>(acc[c]);
+    for (int c = 0; c < G; c++) part[c] = fold_lane2<VEC>(acc[c]);
 }
 
 // Transposed butterfly: reduces G per-lane partials across the warp with the additions of the
@@ -210,11 +224,11 @@ __device__ __forceinline__ void group_distance2(const char *__restrict__ vecs, u
 {
     constexpr int VEC = Vec<T>::VEC;
     constexpr bool HALF = sizeof(T) == 2;
-    float acc0[G][VEC], acc1[G][VEC];
+    f32x2 acc0[G][VEC / 2], acc1[G][VEC / 2];
 #pragma unroll
     for (int c = 0; c < G; c++)
 #pragma unroll
-        for (int k = 0; k < VEC; k++) { acc0[c][k] = 0.0f; acc1[c][k] = 0.0f; }
+        for (int k = 0; k < VEC / 2; k++) { acc0[c][k] = 0ull; acc1[c][k] = 0ull; }
     const char *rp[G];
 #pragma unroll
     for (int c = 0; c < G; c++) rp[c] = vecs + (uint64_t) (uint32_t) ids[c] * row_bytes + 16 * lane;
@@ -262,7 +276,7 @@ __device__ __forceinline__ void group_distance2(const char *__restrict__ vecs, u
     }
     float part0[G], part1[G];
 #pragma unroll
-    for (int c = 0; c < G; c++) { part0[c] = fold_lane<VEC>(acc0[c]); part1[c] = fold_lane<VEC>(acc1[c]); }
+    for (int c = 0; c < G; c++) { part0[c] = fold_lane2<VEC>(acc0[c]); part1[c] = fold_lane2<VEC>(acc1[c]); }
     const float s0 = XReduce<G>::run(part0, lane, 16), s1 = XReduce<G>::run(part1, lane, 16);
     out0 = IP == 1 ? -s0 : s0;
     out1 = IP == 1 ? -s1 : s1;

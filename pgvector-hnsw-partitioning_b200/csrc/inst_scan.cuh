@@ -3,6 +3,7 @@
 // parallel.
 #include "index.h"
 #include "scan_kernel.cuh"
+#include "scan_reg.cuh"
 
 namespace hb {
 cudaError_t HB_CAT(scan_fast_, HBI_NAME)(const ScanParams &p, int sms, int mg, cudaStream_t s, ScanLaunchInfo *i)
@@ -12,6 +13,10 @@ cudaError_t HB_CAT(scan_fast_, HBI_NAME)(const ScanParams &p, int sms, int mg, c
 cudaError_t HB_CAT(scan_slow_, HBI_NAME)(const ScanParams &p, int sms, int mg, cudaStream_t s, ScanLaunchInfo *i)
 {
     return launch_scan_t<HBI_T, HBI_IP, true>(p, sms, mg, s, i);
+}
+cudaError_t HB_CAT(scan_reg_, HBI_NAME)(const ScanParams &p, int R, int sms, int mg, cudaStream_t s, ScanLaunchInfo *i)
+{
+    return launch_scan_reg_t<HBI_T, HBI_IP>(p, R, sms, mg, s, i);
 }
 cudaError_t HB_CAT(dist_, HBI_NAME)(const DistBatchParams &p, cudaStream_t s) { return launch_dist_t<HBI_T, HBI_IP>(p, s); }
 }   // namespace hb

@@ -322,3 +322,50 @@ def test_limits(oracle, pkg, dim, dtype, m, ef):
     with pytest.raises(pkg.HnswError):
         ix2 = pkg.HnswIndex(8, "vector_l2_ops", 8, 32, capacity=10)
         ix2.search(np.zeros((1, 8), np.float32), 5, 1001)       # hnsw.ef_search is capped at 1000
+
+
+# ---- the register-list scan kernel (csrc/scan_reg.cuh): rows of 32 or 64 chunks --------------------
+@pytest.mark.parametrize("dim,dtype,metric,m,ef", [
+    (128, 0, 0, 16, 48), (128, 0, 0, 16, 49), (128, 0, 1, 16, 104), (128, 0, 2, 16, 105), (128, 0, 0, 24, 40),
+    (256, 0, 0, 16, 40), (256, 0, 2, 12, 90), (256, 1, 0, 16, 40), (512, 1, 1, 16, 64), (256, 1, 2, 16, 30)])
+def test_register_list_scan(oracle, pkg, dim, dtype, metric, m, ef):
+    """ef at the edges of the 64- and 128-entry register lists (48|49, 104|105), degrees beyond one warp (m = 24),
+    fp32 and halfvec rows, all metrics; integer-valued data so that exact ties sit at the ef boundary.  The
+    forced shared-memory-list kernel (variant 9) must agree as well."""
+    dt = np.float16 if dtype else np.float32
+    x = sift_like(5000, dim, seed=dim + ef).astype(dt)
+    q = sift_like(200, dim, seed=dim + ef + 1).astype(dt)
+    orc, ix = make(oracle, pkg, x, metric, dtype=dtype, m=m, efc=max(2 * m, 64))
+    check_scan(oracle, orc, ix, q, ef, natural_check=False)
+    e1, d1, c1 = ix.search_elements(q, ef)
+    ix.set_option("variant", 9)
+    e2, d2, c2 = ix.search_elements(q, ef)
+    assert (e1 == e2).all() and (d1.view(np.uint32) == d2.view(np.uint32)).all() and (c1 == c2).all()
+    ix.close()
+
+
+def test_register_list_scan_l1(oracle, pkg):
+    x = sift_like(4000, 128, seed=3)
+    q = sift_like(150, 128, seed=4)
+    orc = oracle.Index(128, 16, 64, oracle.L1, 0, oracle.CANON, seed=2)
+    orc.build(x)
+    ix = pkg.HnswIndex(128, "vector_l1_ops", 16, 64, capacity=4000, seed=2)
+    ix.load_graph(orc.export())
+    check_scan(oracle, orc, ix, q, 40, natural_check=False)
+    ix.close()
+
+
+def test_register_list_tail_and_table_overflow(oracle, pkg):
+    """128-d rows whose distances tie massively (lattice points padded with zeros): the tie tail outgrows the
+    64 register slots -> those queries re-run on the long-list path; a tiny visited table spills to HBM."""
+    rng = np.random.default_rng(6)
+    lat = np.array([[(i >> b) & 1 for b in range(12)] for i in range(4096)], np.float32)[rng.permutation(4096)]
+    x = np.zeros((4096, 128), np.float32)
+    x[:, :12] = lat
+    q = x[rng.integers(0, 4096, 60)]
+    orc, ix = make(oracle, pkg, x, oracle.L2, m=8, efc=32)
+    c = check_scan(oracle, orc, ix, q, 40, natural_check=False)
+    assert c["n_slow"] > 0
+    ix.set_option("slots", 64)
+    check_scan(oracle, orc, ix, q, 30, natural_check=False)
+    ix.close()
