@@ -484,6 +484,7 @@ def main():
             e_ = torch.empty((nq_eval, ef), dtype=torch.int32, device=dev)
             d_ = torch.empty((nq_eval, ef), dtype=torch.float32, device=dev)
             c_ = torch.empty((nq_eval,), dtype=torch.int32, device=dev)
+            ix.counters(reset=True)
             ix.search_dev(q_eval.data_ptr(), nq_eval, ef, e_.data_ptr(), d_.data_ptr(), c_.data_ptr(), stream)
             torch.cuda.synchronize()
             parity = parity_record(par, e_.cpu().numpy(), d_.cpu().numpy())

@@ -88,8 +88,17 @@ int64_t hb_insert(hb_index *ix, const void *host_vecs, int64_t n, const int64_t 
 int hb_index_reserve(hb_index *ix, int64_t capacity);
 /* ambulkdelete, first pass (hnswvacuum.c RemoveHeapTids): the given heap TIDs leave the index; an
  * element left without TIDs keeps routing searches and returns nothing.  Returns the number of TIDs
- * removed.  The graph-repair passes of pgvector's vacuum are not implemented. */
+ * removed. */
 int64_t hb_bulk_delete(hb_index *ix, const int64_t *dead_tids, int64_t n_dead);
+/* ambulkdelete, second and third pass (hnswvacuum.c RepairGraph + MarkDeleted): every element that points at an
+ * emptied element (or whose layer-0 list is not full) gets its neighbours recomputed -- a search in which
+ * emptied elements are walked through but do not count towards ef_construction (+1, it finds itself) -- and is
+ * re-linked (HnswUpdateNeighborsOnDisk with checkExisting); the entry point is repaired first, or replaced by
+ * the highest live element when it was emptied; then the emptied elements lose their lists and their vector.
+ * Returns the number of elements marked deleted; *repaired (may be NULL) = elements re-linked.  Option
+ * "vacuum_batch": elements repaired concurrently (default 2048; 1 = one after the other, the graph is then the
+ * sequential algorithm's).  Slots of deleted elements are not reused by later inserts. */
+int64_t hb_vacuum_repair(hb_index *ix, int64_t *repaired);
 /* Free the memory only inserts use (cached neighbour distances, the pair-distance cache -- 2 kB per
  * element at m = 16 --, batch workspaces), as pgvector frees its in-memory build state when CREATE
  * INDEX ends.  Scans are unaffected; a later hb_insert allocates what it needs again. */

@@ -54,6 +54,7 @@ struct OrcIndex {
     int32_t *nbru; float *nbrud; uint8_t *cntu;         /* urows x m */
     int64_t urows, ucap;
     uint8_t *ntids; int64_t *tids;                      /* n x ORC_HEAPTIDS */
+    uint8_t *deleted;                                   /* HnswElementTupleData.deleted (set by vacuum's MarkDeleted) */
     int32_t entry; int entry_level;
     OrcCounters ctr;
 };
@@ -543,7 +544,7 @@ void orc_free(OrcIndex *ix)
 {
     if (!ix) return;
     free(ix->vecs); free(ix->level); free(ix->nbr0); free(ix->nbr0d); free(ix->cnt0);
-    free(ix->uoff); free(ix->nbru); free(ix->nbrud); free(ix->cntu); free(ix->ntids); free(ix->tids);
+    free(ix->uoff); free(ix->nbru); free(ix->nbrud); free(ix->cntu); free(ix->ntids); free(ix->tids); free(ix->deleted);
     free(ix);
 }
 
@@ -560,6 +561,8 @@ static void grow_elems(OrcIndex *ix, int64_t need)
     ix->cnt0 = (uint8_t *) realloc(ix->cnt0, cap);
     ix->uoff = (int32_t *) realloc(ix->uoff, sizeof(int32_t) * cap);
     ix->ntids = (uint8_t *) realloc(ix->ntids, cap);
+    ix->deleted = (uint8_t *) realloc(ix->deleted, cap);
+    memset(ix->deleted + ix->cap, 0, (size_t) (cap - ix->cap));
     ix->tids = (int64_t *) realloc(ix->tids, sizeof(int64_t) * cap * ORC_HEAPTIDS);
     ix->cap = cap;
 }
@@ -672,6 +675,224 @@ int64_t orc_build(OrcIndex *ix, const void *vecs, int64_t n, const int64_t *heap
         if (r == -2) return -2;
     }
     return ix->n;
+}
+
+
+/* ------------------------------------------------------------------ vacuum (hnswvacuum.c) */
+/* ambulkdelete upstream = RemoveHeapTids, RepairGraph, MarkDeleted [RECALL].  orc_bulk_delete is the first pass,
+ * orc_vacuum_repair the second and third. */
+
+static int cmp_i64(const void *a, const void *b)
+{
+    int64_t x = *(const int64_t *) a, y = *(const int64_t *) b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+/* RemoveHeapTids: dead heap TIDs leave their elements (the remaining TIDs keep their order); returns how many left */
+int64_t orc_bulk_delete(OrcIndex *ix, const int64_t *dead_tids, int64_t n_dead)
+{
+    if (n_dead <= 0) return 0;
+    int64_t *dead = (int64_t *) malloc(sizeof(int64_t) * n_dead);
+    memcpy(dead, dead_tids, sizeof(int64_t) * n_dead);
+    qsort(dead, n_dead, sizeof(int64_t), cmp_i64);
+    int64_t removed = 0;
+    for (int64_t e = 0; e < ix->n; e++) {
+        int64_t *t = ix->tids + e * ORC_HEAPTIDS;
+        int nt = ix->ntids[e], w = 0;
+        for (int k = 0; k < nt; k++)
+            if (!bsearch(&t[k], dead, n_dead, sizeof(int64_t), cmp_i64)) t[w++] = t[k];
+        for (int k = w; k < nt; k++) t[k] = 0;
+        removed += nt - w;
+        ix->ntids[e] = (uint8_t) w;
+    }
+    free(dead);
+    return removed;
+}
+
+/* HnswSearchLayer as vacuum calls it (skipElement != NULL): elements left without heap TIDs are traversed and
+ * kept in W but do not count towards ef (CountElement); wlen is never decremented ("No need to decrement wlen"),
+ * so from the first overflow on every counted admission evicts the furthest entry, whatever it is. */
+static int search_layer_vacuum(const OrcIndex *ix, const float *q, const Cand *ep, int nep, int ef, int lc, Cand **out,
+                               int *out_cap, Scratch *s, OrcCounters *ctr)
+{
+    scratch_begin(s, ix->n, ef > nep ? ef : nep);
+    int wlen = 0;
+    for (int i = 0; i < nep; i++) {
+        s->stamp[ep[i].id] = s->epoch;
+        c_push(s, ep[i]);
+        if (s->nW + 2 > s->capW) { s->capW = 2 * s->capW + 2; s->W = (Cand *) realloc(s->W, sizeof(Cand) * s->capW); }
+        w_push(s, ep[i]);
+        if (ix->ntids[ep[i].id] != 0) wlen++;
+    }
+    while (s->nC > 0) {
+        Cand c = c_pop(s);
+        Cand f = s->W[0];
+        if (c.d > f.d) break;
+        if (ctr) { if (lc == 0) ctr->n_hop0++; else ctr->n_hopu++; }
+        uint8_t *cnt;
+        const int32_t *nb = nbrs(ix, c.id, lc, NULL, &cnt);
+        for (int i = 0; i < *cnt; i++) {
+            int32_t e = nb[i];
+            if (s->stamp[e] == s->epoch) continue;
+            s->stamp[e] = s->epoch;
+            int always = wlen < ef;
+            f = s->W[0];
+            float ed = dist_q_row(ix, q, row_of(ix, e));
+            if (ctr) ctr->n_dist++;
+            Cand ec = { ed, e };
+            if (ed < f.d || always) {
+                c_push(s, ec);
+                if (s->nW + 2 > s->capW) { s->capW = 2 * s->capW + 2; s->W = (Cand *) realloc(s->W, sizeof(Cand) * s->capW); }
+                w_push(s, ec);
+                if (ix->ntids[e] != 0) {
+                    wlen++;
+                    if (wlen > ef) (void) w_pop(s);
+                }
+            }
+        }
+    }
+    int cnt = s->nW;
+    if (*out_cap < cnt + 1) { *out_cap = cnt + 64; *out = (Cand *) realloc(*out, sizeof(Cand) * *out_cap); }
+    for (int i = cnt - 1; i >= 0; i--) (*out)[i] = w_pop(s);
+    return cnt;
+}
+
+/* NeedsUpdated: a neighbour is being deleted, or layer 0 is not full */
+static int needs_updated(const OrcIndex *ix, int64_t e)
+{
+    for (int lc = ix->level[e]; lc >= 0; lc--) {
+        uint8_t *cnt;
+        const int32_t *nb = nbrs(ix, e, lc, NULL, &cnt);
+        for (int i = 0; i < *cnt; i++)
+            if (ix->ntids[nb[i]] == 0) return 1;
+    }
+    return ix->cnt0[e] < 2 * ix->m;
+}
+
+/* HnswUpdateNeighborsOnDisk (checkExisting = true) for one neighbour: HnswUpdateConnection on the list as stored,
+ * distances recomputed, a neighbour that is being deleted is replaced before any heuristic selection */
+static void update_connection_vacuum(OrcIndex *ix, int32_t e, float d, int32_t n, int lm, int lc, OrcCounters *ctr)
+{
+    float *nd; uint8_t *cnt;
+    int32_t *nb = nbrs(ix, n, lc, &nd, &cnt);
+    for (int i = 0; i < *cnt; i++) if (nb[i] == e) return;           /* existing connection */
+    if (*cnt < lm) { nb[*cnt] = e; nd[*cnt] = d; (*cnt)++; return; }
+    Cand c[lm + 1], r[lm + 1], pruned;
+    int have = 0;
+    for (int i = 0; i < lm; i++) {
+        c[i].id = nb[i];
+        c[i].d = dist_elems(ix, n, nb[i], ctr);
+        nd[i] = c[i].d;
+        if (ix->ntids[nb[i]] == 0) { pruned = c[i]; have = 1; break; }      /* prune element if being deleted */
+    }
+    if (!have) {
+        c[lm].id = e; c[lm].d = d;
+        qsort(c, lm + 1, sizeof(Cand), cmp_cand);
+        select_neighbors(ix, c, lm + 1, lm, r, &pruned, ctr);
+    }
+    for (int i = 0; i < lm; i++)
+        if (nb[i] == pruned.id) { nb[i] = e; nd[i] = d; break; }
+}
+
+/* RepairGraphElement */
+static void repair_element(OrcIndex *ix, int64_t e, int32_t entry, Scratch *s, OrcCounters *ctr)
+{
+    if (entry >= 0 && e == entry) return;
+    int m = ix->m, level = ix->level[e];
+    int nl = level + 1;
+    Cand *sel[nl]; int nsel[nl];
+    for (int lc = 0; lc < nl; lc++) { sel[lc] = (Cand *) malloc(sizeof(Cand) * (2 * m + 1)); nsel[lc] = 0; }
+    if (entry >= 0) {
+        /* HnswFindElementNeighbors(existing = true): the element's stored lists are still in the graph while it searches */
+        float q[ix->dim];
+        row_as_float(ix, e, q);
+        int cap_ep = 64, cap_w = 64, nep = 1;
+        Cand *ep = (Cand *) malloc(sizeof(Cand) * cap_ep), *w = (Cand *) malloc(sizeof(Cand) * cap_w);
+        ep[0].id = entry;
+        ep[0].d = dist_q_row(ix, q, row_of(ix, entry));
+        if (ctr) ctr->n_dist++;
+        int entry_level = ix->level[entry];
+        for (int lc = entry_level; lc >= level + 1; lc--) {
+            int nw = search_layer_vacuum(ix, q, ep, nep, 1, lc, &w, &cap_w, s, ctr);
+            if (cap_ep < nw + 1) { cap_ep = nw + 64; ep = (Cand *) realloc(ep, sizeof(Cand) * cap_ep); }
+            memcpy(ep, w, sizeof(Cand) * nw); nep = nw;
+        }
+        int top = level > entry_level ? entry_level : level;
+        for (int lc = top; lc >= 0; lc--) {
+            int lm = layer_m(ix, lc);
+            int nw = search_layer_vacuum(ix, q, ep, nep, ix->efc + 1, lc, &w, &cap_w, s, ctr);   /* "Add one for existing element" */
+            /* RemoveElements: the element itself and elements being deleted help the search but are not candidates */
+            Cand lw[nw + 1];
+            int nlw = 0;
+            for (int i = 0; i < nw; i++)
+                if (w[i].id != e && ix->ntids[w[i].id] != 0) lw[nlw++] = w[i];
+            nsel[lc] = select_neighbors(ix, lw, nlw, lm, sel[lc], NULL, ctr);
+            if (cap_ep < nw + 1) { cap_ep = nw + 64; ep = (Cand *) realloc(ep, sizeof(Cand) * cap_ep); }
+            memcpy(ep, w, sizeof(Cand) * nw); nep = nw;
+        }
+        free(ep); free(w);
+    }
+    /* overwrite the neighbour tuple (HnswInitNeighbors emptied every layer first) */
+    for (int lc = 0; lc < nl; lc++) {
+        float *nd; uint8_t *cnt;
+        int32_t *nb = nbrs(ix, e, lc, &nd, &cnt);
+        int lm = layer_m(ix, lc);
+        for (int i = 0; i < lm; i++) { nb[i] = i < nsel[lc] ? sel[lc][i].id : -1; nd[i] = i < nsel[lc] ? sel[lc][i].d : 0.0f; }
+        *cnt = (uint8_t) nsel[lc];
+    }
+    for (int lc = level; lc >= 0; lc--) {
+        int lm = layer_m(ix, lc);
+        for (int i = 0; i < nsel[lc]; i++)
+            update_connection_vacuum(ix, (int32_t) e, sel[lc][i].d, sel[lc][i].id, lm, lc, ctr);
+    }
+    for (int lc = 0; lc < nl; lc++) free(sel[lc]);
+}
+
+/* RepairGraph (entry point first, then every element in page order) + MarkDeleted.  Returns the number of
+ * elements marked deleted by this call; *repaired (nullable) = elements whose neighbours were recomputed. */
+int64_t orc_vacuum_repair(OrcIndex *ix, int64_t *repaired)
+{
+    Scratch s; scratch_init(&s);
+    OrcCounters *ctr = &ix->ctr;
+    int64_t nrep = 0;
+    /* the highest live element that is not the entry point (RemoveHeapTids remembers it; first one in page order) */
+    int32_t highest = -1; int hl = -1;
+    for (int64_t e = 0; e < ix->n; e++)
+        if (ix->ntids[e] != 0 && e != ix->entry && ix->level[e] > hl) { highest = (int32_t) e; hl = ix->level[e]; }
+    /* RepairGraphEntryPoint */
+    if (highest >= 0 && needs_updated(ix, highest)) { repair_element(ix, highest, ix->entry, &s, ctr); nrep++; }
+    if (ix->entry >= 0) {
+        if (ix->ntids[ix->entry] == 0) {
+            ix->entry = highest;
+            ix->entry_level = highest >= 0 ? ix->level[highest] : -1;
+        } else if (needs_updated(ix, ix->entry)) { repair_element(ix, ix->entry, highest, &s, ctr); nrep++; }
+    }
+    for (int64_t e = 0; e < ix->n; e++) {
+        if (ix->ntids[e] == 0) continue;
+        if (!needs_updated(ix, e)) continue;
+        if (e == ix->entry) continue;
+        repair_element(ix, e, ix->entry, &s, ctr);
+        nrep++;
+    }
+    /* MarkDeleted: the emptied elements leave the graph for good */
+    int64_t marked = 0;
+    size_t rowb = (size_t) ix->dim * ix->esize;
+    for (int64_t e = 0; e < ix->n; e++) {
+        if (ix->ntids[e] != 0 || ix->deleted[e]) continue;
+        ix->deleted[e] = 1;
+        marked++;
+        memset(ix->vecs + (size_t) e * rowb, 0, rowb);
+        for (int lc = ix->level[e]; lc >= 0; lc--) {
+            float *nd; uint8_t *cnt;
+            int32_t *nb = nbrs(ix, e, lc, &nd, &cnt);
+            int lm = layer_m(ix, lc);
+            for (int i = 0; i < lm; i++) { nb[i] = -1; nd[i] = 0.0f; }
+            *cnt = 0;
+        }
+    }
+    scratch_free(&s);
+    if (repaired) *repaired = nrep;
+    return marked;
 }
 
 /* ------------------------------------------------------------------ scan */

@@ -58,6 +58,14 @@ uint64_t orc_splitmix64(uint64_t x);
 int64_t orc_insert(OrcIndex *ix, const void *vec, int64_t heap_tid);
 int64_t orc_build(OrcIndex *ix, const void *vecs, int64_t n, const int64_t *heap_tids);
 
+/* hnswvacuum.c [RECALL]: ambulkdelete = RemoveHeapTids (orc_bulk_delete: returns the TIDs removed), then
+ * RepairGraph + MarkDeleted (orc_vacuum_repair: elements without heap TIDs stop counting towards ef, every element
+ * that points at one -- or whose layer 0 is not full -- gets its neighbours recomputed (HnswFindElementNeighbors with
+ * existing = true) and re-linked, the entry point moves if it was deleted; then the emptied elements are unlinked
+ * and zeroed.  Returns the number of elements marked deleted; *repaired = elements re-linked). */
+int64_t orc_bulk_delete(OrcIndex *ix, const int64_t *dead_tids, int64_t n_dead);
+int64_t orc_vacuum_repair(OrcIndex *ix, int64_t *repaired);
+
 /* hnswscan.c GetScanItems: entry -> greedy descent (ef=1) -> layer-0 search (ef_search).
  * Writes up to ef (element, distance) pairs nearest-first; returns the count. */
 int orc_search_elements(const OrcIndex *ix, const void *query, int ef, int32_t *out_elem,

@@ -60,6 +60,10 @@ def lib():
     L.orc_insert.argtypes = [C.c_void_p, vp, C.c_int64]
     L.orc_build.restype = C.c_int64
     L.orc_build.argtypes = [C.c_void_p, vp, C.c_int64, i64p]
+    L.orc_bulk_delete.restype = C.c_int64
+    L.orc_bulk_delete.argtypes = [C.c_void_p, i64p, C.c_int64]
+    L.orc_vacuum_repair.restype = C.c_int64
+    L.orc_vacuum_repair.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     L.orc_search_elements.restype = C.c_int
     L.orc_search_elements.argtypes = [C.c_void_p, vp, C.c_int, i32p, f32p, C.POINTER(Counters)]
     L.orc_search_tids.restype = C.c_int
@@ -172,6 +176,17 @@ class Index:
         vecs = self._q(vecs)
         t = None if tids is None else np.ascontiguousarray(tids, np.int64)
         return int(lib().orc_build(self._h, _p(vecs), vecs.shape[0], _p(t)))
+
+    def bulk_delete(self, dead_tids):
+        """hnswvacuum.c RemoveHeapTids -> number of heap TIDs removed"""
+        t = np.ascontiguousarray(dead_tids, np.int64)
+        return int(lib().orc_bulk_delete(self._h, _p(t), t.size))
+
+    def vacuum_repair(self):
+        """hnswvacuum.c RepairGraph + MarkDeleted -> (elements marked deleted, elements re-linked)"""
+        rep = C.c_int64()
+        marked = int(lib().orc_vacuum_repair(self._h, C.byref(rep)))
+        return marked, int(rep.value)
 
     def build_counters(self):
         c = Counters()

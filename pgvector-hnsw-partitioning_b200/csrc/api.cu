@@ -335,6 +335,7 @@ int hb_set_option(hb_index *ix, const char *name, int value)
     else if (!strcmp(name, "eval_table")) ix->opt_eval_table = value;
     else if (!strcmp(name, "build_fraction")) ix->opt_build_fraction = value > 0 ? value : 16;
     else if (!strcmp(name, "auto_grow")) ix->opt_auto_grow = value;
+    else if (!strcmp(name, "vacuum_batch")) ix->opt_vacuum_batch = value;
     else { set_error("hb_set_option: unknown option %s", name); return HB_EINVAL; }
     return HB_OK;
 }
@@ -504,6 +505,7 @@ int hb_index_load(hb_index *ix, int64_t n, int64_t upper_rows, int32_t entry, co
     ix->entry_level = ix->entry >= 0 ? level[ix->entry] : -1;
     ix->h_level.assign(level, level + n);
     ix->h_ntids.assign(n, 1);
+    ix->h_deleted.clear();
     if (ntids) ix->h_ntids.assign(ntids, ntids + n);
     ix->h_tids.assign((size_t) n * HB_HEAPTIDS, 0);
     for (int64_t i = 0; i < n; i++) {

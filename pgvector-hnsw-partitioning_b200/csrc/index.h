@@ -98,12 +98,14 @@ struct hb_index {
     // host mirrors of the small per-element state
     std::vector<uint8_t> h_level, h_ntids;
     std::vector<int64_t> h_tids;   // n x HB_HEAPTIDS
+    std::vector<uint8_t> h_deleted;   // HnswElementTupleData.deleted: set by hb_vacuum_repair's MarkDeleted (may be shorter than n)
 
     // tuning knobs (0 = automatic)
     int opt_slots = 0, opt_grid = 0, opt_build_batch = 0, opt_per_query = 0, opt_variant = 0, opt_no_slow = 0;
     int opt_pair_cache = 1, opt_pair_fill = 1, opt_fused_select = 1, opt_eval_table = 1;
     int opt_auto_grow = 1;         // inserts beyond the capacity grow the index (hb_index_reserve) instead of failing
     int opt_build_fraction = 16;   // a batch is at most 1/opt_build_fraction of the graph
+    int opt_vacuum_batch = 0;      // elements repaired concurrently by hb_vacuum_repair (0 = 2048, 1 = one after the other)
     int opt_link_kernel = 0;       // 0 automatic, 1 warp-per-segment, 2 CTA-per-segment (link_kernel.cuh)
 
     // workspaces

@@ -73,6 +73,7 @@ _SIGS = {
     "hb_index_trim": (C.c_int, [C.c_void_p]),
     "hb_index_reserve": (C.c_int, [C.c_void_p, C.c_int64]),
     "hb_bulk_delete": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "hb_vacuum_repair": (C.c_int64, [C.c_void_p, C.c_void_p]),
     "hb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "hb_level_for": (C.c_int, [C.c_uint64, C.c_int64, C.c_int]),
     "hb_index_load": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32] + [C.c_void_p] * 7),
@@ -254,6 +255,12 @@ class HnswIndex:
         """ambulkdelete, first pass: remove heap TIDs; returns how many were removed"""
         t = np.ascontiguousarray(dead_tids, np.int64)
         return self._ck(self._L.hb_bulk_delete(self._h, _p(t), t.size), "hb_bulk_delete")
+
+    def vacuum_repair(self):
+        """ambulkdelete, passes 2 and 3 (RepairGraph + MarkDeleted) -> (elements marked deleted, elements re-linked)"""
+        rep = C.c_int64()
+        marked = self._ck(self._L.hb_vacuum_repair(self._h, C.byref(rep)), "hb_vacuum_repair")
+        return int(marked), int(rep.value)
 
     def reserve(self, capacity):
         self._ck(self._L.hb_index_reserve(self._h, capacity), "hb_index_reserve")

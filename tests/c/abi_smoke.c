@@ -12,7 +12,7 @@ int main(void)
     int n_syms = 0;
     REF(hb_last_error); REF(hb_version); REF(hb_device_count);
     REF(hb_index_create); REF(hb_index_free); REF(hb_index_size); REF(hb_index_entry);
-    REF(hb_build); REF(hb_insert); REF(hb_index_reserve); REF(hb_bulk_delete); REF(hb_index_trim); REF(hb_set_build_batch); REF(hb_level_for); REF(hb_set_option);
+    REF(hb_build); REF(hb_insert); REF(hb_index_reserve); REF(hb_bulk_delete); REF(hb_vacuum_repair); REF(hb_index_trim); REF(hb_set_build_batch); REF(hb_level_for); REF(hb_set_option);
     REF(hb_index_load); REF(hb_index_load_pgvector_pages); REF(hb_pgvector_pages_info); REF(hb_index_upper_rows); REF(hb_index_export);
     REF(hb_beginscan); REF(hb_rescan); REF(hb_gettuple); REF(hb_endscan); REF(hb_scan_set_iterative);
     REF(hb_iter_begin); REF(hb_iter_next); REF(hb_iter_tuples); REF(hb_iter_end); REF(hb_search_batch_filtered);

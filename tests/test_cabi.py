@@ -111,3 +111,30 @@ def test_c_example_builds(pkg, tmp_path):
     if not has_gpu():
         out = subprocess.run([exe], capture_output=True, text=True)
         assert out.returncode == 1 and "no CUDA device" in out.stderr
+
+
+def test_postgres_glue_compiles_against_the_am_api(tmp_path):
+    """pg/hnsw_b200_am.c (the index-AM glue a maintainer adds) compiles as C against tests/c/pgstub -- a stand-in for
+    the PostgreSQL 16 headers that declares the IndexAmRoutine callbacks with their real signatures -- and against
+    include/hnsw_b200.h, with -Werror: a callback or C-ABI signature that drifts breaks this test.  Every hb_* call
+    the glue makes must resolve against the built library."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    obj = str(tmp_path / "glue.o")
+    cmd = ["gcc", "-std=gnu99", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter", "-DHNSW_B200_WITH_POSTGRES",
+           "-I", os.path.join(root, "tests", "c", "pgstub"), "-I", os.path.join(root, "include"), "-c",
+           os.path.join(root, "pg", "hnsw_b200_am.c"), "-o", obj]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    syms = subprocess.run(["nm", "-u", obj], capture_output=True, text=True).stdout
+    used = sorted(set(re.findall(r"\bU (hb_[a-z0-9_]+)", syms)))
+    assert {"hb_index_create", "hb_insert", "hb_beginscan", "hb_rescan", "hb_gettuple", "hb_endscan", "hb_bulk_delete",
+            "hb_vacuum_repair", "hb_index_trim", "hb_scan_set_iterative"} <= set(used)
+    declared = set(declared_symbols())
+    assert set(used) <= declared
+    defined = subprocess.run(["nm", "-g", "--defined-only", obj], capture_output=True, text=True).stdout
+    assert "hnsw_b200_handler" in defined
+    # without the macro the file is empty (the library build never depends on PostgreSQL)
+    out = subprocess.run(["gcc", "-std=gnu99", "-c", os.path.join(root, "pg", "hnsw_b200_am.c"), "-o", str(tmp_path / "empty.o")],
+                         capture_output=True, text=True)
+    assert out.returncode == 0

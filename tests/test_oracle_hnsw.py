@@ -173,3 +173,38 @@ def test_l1_recall_vs_bruteforce(oracle):
     i = 0
     want = np.abs(x[e[i, 0]].astype(np.float64) - q[i].astype(np.float64)).sum()
     assert abs(d[i, 0] - want) <= 1e-5 * want
+
+
+def test_vacuum_repair_invariants(oracle):
+    """hnswvacuum.c restated (orc_bulk_delete + orc_vacuum_repair): after RepairGraph + MarkDeleted no live element points at a
+    deleted one, deleted elements are unlinked and zeroed, a deleted entry point moves to the highest live element,
+    searches return live tuples only with good recall, and a second vacuum is a no-op."""
+    n, dim = 3000, 24
+    x = clustered(n, dim, 16, seed=1)
+    ix = oracle.Index(dim, 8, 32, oracle.L2, oracle.F32, oracle.CANON, seed=3)
+    ix.build(x)
+    ent, lvl = ix.entry
+    dead = np.unique(np.concatenate([np.arange(0, n, 3), [ent]])).astype(np.int64)
+    assert ix.bulk_delete(dead) == len(dead) and ix.bulk_delete(dead) == 0
+    marked, repaired = ix.vacuum_repair()
+    assert marked == len(dead) and repaired > 0
+    g = ix.export()
+    alive = g.ntids > 0
+    assert alive.sum() == n - len(dead)
+    assert ix.entry[0] != ent and alive[ix.entry[0]]
+    assert g.level[ix.entry[0]] == g.level[alive].max()
+    for e in np.nonzero(alive)[0]:
+        nb = g.nbr0[e][g.nbr0[e] >= 0]
+        assert alive[nb].all()
+        if g.uoff[e] >= 0:
+            for r in range(g.level[e]):
+                nb = g.nbru[g.uoff[e] + r]
+                assert alive[nb[nb >= 0]].all()
+    assert (g.nbr0[~alive] == -1).all() and not g.vecs[~alive].any()
+    q = clustered(100, dim, 16, seed=2)
+    e1, d1, c1, _ = ix.search_batch(q, 40)
+    d2 = ((q[:, None, :] - x[None, alive, :]) ** 2).sum(-1)
+    gt = np.nonzero(alive)[0][np.argsort(d2, axis=1)[:, :10]]
+    assert all(alive[e1[i, :c1[i]]].all() for i in range(100))
+    assert np.mean([len(set(e1[i, :10]) & set(gt[i])) / 10 for i in range(100)]) > 0.95
+    assert ix.vacuum_repair() == (0, 0)

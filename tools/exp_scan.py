@@ -64,6 +64,8 @@ for variant in [int(v) for v in a.variants.split(",")]:
 
         run(0, 3)
         torch.cuda.synchronize()
+        ix.search_dev(q_all[0].data_ptr(), a.nq, a.ef, outs[0][0].data_ptr(), outs[0][1].data_ptr(), outs[0][2].data_ptr(), streams[0].cuda_stream)
+        torch.cuda.synchronize()
         rec = bench.recall_at(outs[0][0][:1000, :10].cpu().numpy(), gt)
         ix.counters(reset=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
