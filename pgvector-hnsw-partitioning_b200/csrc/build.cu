@@ -451,7 +451,8 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         const double t0 = now();
         n_batches++;
         const int64_t cur = ix->n;
-        int64_t b = std::max<int64_t>(1, std::min<int64_t>(auto_batch && cur < 524288 ? 8192 : max_batch, cur / std::max(2, ix->opt_build_fraction)));
+        const int frac = cur < 65536 ? std::max(2, ix->opt_build_fraction_small) : std::max(2, ix->opt_build_fraction);
+        int64_t b = std::max<int64_t>(1, std::min<int64_t>(auto_batch && cur < 524288 ? 8192 : max_batch, cur / frac));
         b = std::min<int64_t>(b, (int64_t) todo.size() - pos);
         levels.resize(b);
         for (int64_t i = 0; i < b; i++) levels[i] = (uint8_t) level_for(ix->seed, ix->seq + i, m);
@@ -735,7 +736,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         if (trace) cudaEventRecord(tev[4], s);
         HB_CK(cudaMemcpyAsync(ix->h_flag, d_flag, 12, cudaMemcpyDeviceToHost, s));
         // while the device works on this batch: the rows of the next one (at most ~cur/16 + a chunk ahead)
-        rc = upload_upto((int64_t) pos + b + std::min<int64_t>(max_batch, (cur + b) / std::max(2, ix->opt_build_fraction) + 1));
+        rc = upload_upto((int64_t) pos + b + std::min<int64_t>(max_batch, (cur + b) / std::max(2, std::min(ix->opt_build_fraction, ix->opt_build_fraction_small)) + 1));
         if (rc) return rc;
         const double t1 = now();
         HB_CK(cudaStreamSynchronize(s));
