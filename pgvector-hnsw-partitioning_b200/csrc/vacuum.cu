@@ -483,12 +483,12 @@ extern "C" int64_t hb_vacuum_repair(hb_index *ix, int64_t *repaired)
         if (ix->h_ntids[e] != 0 && e != ix->entry && ix->h_level[e] > hl) { highest = (int32_t) e; hl = ix->h_level[e]; }
     // RepairGraphEntryPoint
     int rc;
-    if (highest >= 0 && (rc = run_batch({ highest }, ix->entry, ix->entry_level))) return rc;
+    if (highest >= 0 && (rc = run_batch({ highest }, ix->entry, ix->entry_level)) != 0) return rc;
     if (ix->entry >= 0) {
         if (ix->h_ntids[ix->entry] == 0) {
             ix->entry = highest;
             ix->entry_level = highest >= 0 ? ix->h_level[highest] : -1;
-        } else if ((rc = run_batch({ ix->entry }, highest, highest >= 0 ? ix->h_level[highest] : -1))) return rc;
+        } else if ((rc = run_batch({ ix->entry }, highest, highest >= 0 ? ix->h_level[highest] : -1)) != 0) return rc;
     }
     // RepairGraph: every live element in page order
     std::vector<int32_t> batch;
@@ -496,7 +496,7 @@ extern "C" int64_t hb_vacuum_repair(hb_index *ix, int64_t *repaired)
     for (int64_t e = 0; e <= n; e++) {
         if (e < n && ix->h_ntids[e] != 0 && e != ix->entry) batch.push_back((int32_t) e);
         if ((int) batch.size() == bmax || (e == n && !batch.empty())) {
-            if ((rc = run_batch(batch, ix->entry, ix->entry_level))) return rc;
+            if ((rc = run_batch(batch, ix->entry, ix->entry_level)) != 0) return rc;
             batch.clear();
         }
     }
