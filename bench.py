@@ -52,6 +52,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_JSON_FD = None
+
+
+def own_stdout():
+    """stdout must carry the one JSON line and nothing else, but native libraries write there too (NCCL prints its
+    version banner at the first communicator): keep the real stdout aside for emit() and point fd 1 at stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -302,6 +324,7 @@ def main():
 
     if args.impl == "reference" and rank != 0:
         return 0
+    own_stdout()
     # stdout carries the one JSON line and nothing else: NCCL's banner ("NCCL version ...") goes to stderr
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
@@ -310,7 +333,7 @@ def main():
 
     if not torch.cuda.is_available():
         if args.impl == "reference":
-            print(json.dumps({"impl": "reference", "unavailable": "no CUDA device to build the 1M-element graph the CPU path searches"}))
+            emit({"impl": "reference", "unavailable": "no CUDA device to build the 1M-element graph the CPU path searches"})
             return 0
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
 
@@ -327,12 +350,12 @@ def main():
     if args.workload == "partitioned" and args.impl == "ours":
         rec = run_partitioned(args, ctx, args.n, args.dim if args.dim != 768 else 128)
         if rank == 0:
-            print(json.dumps(standalone_line(rec, world, args)))
+            emit(standalone_line(rec, world, args))
         return finish(torch, world)
     if args.workload == "build" and args.impl == "ours":
         rec = run_build_partitioned(args, ctx, args.n, args.dim if args.dim != 768 else 1536)
         if rank == 0:
-            print(json.dumps(standalone_line(rec, world, args)))
+            emit(standalone_line(rec, world, args))
         return finish(torch, world)
 
     # ---------------------------------------------------------------- data + index (untimed)
@@ -550,7 +573,7 @@ def main():
             line["partitioned"] = part
             line["build_partitioned"] = bpart
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     return finish(torch, world)
 
 
@@ -599,7 +622,7 @@ def run_reference(args, ix, q_eval, ef, rec, n, dim, nq):
             "cpu_baseline": cb,
             "e2e": {"value": round(qps, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 

@@ -12,7 +12,7 @@
 namespace hb {
 
 constexpr int SCAN_WARPS = 4;   // warps (= concurrent queries) per CTA
-constexpr int MAX_CTAS_PER_SM = 8;   // cap on resident CTAs per SM (sizes the per-warp overflow tables)
+constexpr int MAX_CTAS_PER_SM = 12;   // cap on resident CTAs per SM (sizes the per-warp overflow tables)
 
 struct ScanParams {
     GraphView g;

@@ -342,6 +342,15 @@ template <typename T, int IP>
 cudaError_t launch_scan_reg_t(const ScanParams &p, int R, int num_sms, int max_grid, cudaStream_t stream, ScanLaunchInfo *info)
 {
     const int nv = nv_of(p.g.nvec);
+    if (nv == 1 && R == 2 && p.variant) {       // occupancy experiments (hb_set_option "variant")
+        switch (p.variant) {
+        case 1: return launch_scan_reg_variant<T, IP, 1, 8, 2, 8>(p, num_sms, max_grid, stream, info);
+        case 2: return launch_scan_reg_variant<T, IP, 1, 4, 2, 8>(p, num_sms, max_grid, stream, info);
+        case 3: return launch_scan_reg_variant<T, IP, 1, 4, 2, 10>(p, num_sms, max_grid, stream, info);
+        case 4: return launch_scan_reg_variant<T, IP, 1, 2, 2, 12>(p, num_sms, max_grid, stream, info);
+        default: break;
+        }
+    }
     if (nv == 1 && R == 2) return launch_scan_reg_variant<T, IP, 1, 8, 2, 6>(p, num_sms, max_grid, stream, info);
     if (nv == 1 && R == 4) return launch_scan_reg_variant<T, IP, 1, 8, 4, 6>(p, num_sms, max_grid, stream, info);
     if (nv == 2 && R == 2) return launch_scan_reg_variant<T, IP, 2, 8, 2, 4>(p, num_sms, max_grid, stream, info);

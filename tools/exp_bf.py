@@ -3,7 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import pgvector_hnsw_partitioning_b200 as pkg
-from bench import gen_set, exact_topk, recall_at
+from bench import gen_set, exact_topk_metric, recall_at
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 nq = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
@@ -27,5 +27,5 @@ for it in range(3):
     tf = 2.0 * nq * n * dim / (st["gemm_ms"] * 1e-3) / 1e12
     print("iter %d: total %.1f ms, gemm %.2f ms = %.0f TFLOP/s, certified %d rescanned %d, %.0f QPS (whole call)" %
           (it, dt * 1e3, st["gemm_ms"], tf, st["certified"], st["rescanned"], nq / dt), flush=True)
-gt = exact_topk(x, q[:1000], 10)
+gt = exact_topk_metric(x, q[:1000], 10, "cosine")
 print("agreement with torch fp32 top-10:", recall_at(elem[:1000], gt))

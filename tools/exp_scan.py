@@ -25,6 +25,7 @@ ap.add_argument("--variants", default="0")
 ap.add_argument("--streams", default="1,3")
 ap.add_argument("--latency", action="store_true", help="also time single scans through hb_rescan + hb_gettuple")
 ap.add_argument("--seed", type=int, default=20260103)
+ap.add_argument("--slots", type=int, default=0, help="visited-table slots (0 = automatic)")
 a = ap.parse_args()
 
 dev = torch.device("cuda", 0)
@@ -45,6 +46,8 @@ q_all = q_all.view(nsteps + 3, a.nq, a.dim)
 metric = "l2" if "_l2_" in opc else ("ip" if "_ip_" in opc else "cosine")
 gt = bench.exact_topk_metric(xs, q_all[0][:1000], 10, metric)
 del x, xs
+if a.slots:
+    ix.set_option("slots", a.slots)
 for variant in [int(v) for v in a.variants.split(",")]:
     ix.set_option("variant", variant)
     for ns in [int(s) for s in a.streams.split(",")]:
