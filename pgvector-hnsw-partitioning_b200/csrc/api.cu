@@ -563,7 +563,7 @@ static int choose_slots(const hb_index *ix, int ef, int capW)
     // spill into the per-warp overflow table in HBM.
     const size_t fixed = (size_t) ix->nvec * (ix->dtype == HB_F32 ? 4 : 8) * 4 + (size_t) capW * 8 + 16;
     int slots;
-    if (ix->opt_slots > 0) slots = pow2ceil(ix->opt_slots);
+    if (ix->opt_slots > 0) slots = (ix->opt_slots + 15) & ~15;          // any multiple of 16 (the home slot is a mulhi, not a mask)
     else {
         slots = std::max(1024, pow2ceil(ef * 16));
         const int cap = pow2ceil(ef * 64);

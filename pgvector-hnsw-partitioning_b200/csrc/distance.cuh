@@ -140,9 +140,11 @@ __device__ __forceinline__ void group_partials(const char *__restrict__ vecs, ui
     for (int c = 0; c < G; c++)
 #pragma unroll
         for (int k = 0; k < VEC / 2; k++) acc[c][k] = 0ull;
+    // row address = (base + this lane's chunk) + id * row_bytes: one multiply-add with a 64-bit addend per row
+    const char *lane_base = vecs + 16 * lane;
     const char *rp[G];
 #pragma unroll
-    for (int c = 0; c < G; c++) rp[c] = vecs + (uint64_t) (uint32_t) ids[c] * row_bytes + 16 * lane;
+    for (int c = 0; c < G; c++) rp[c] = lane_base + (uint64_t) (uint32_t) ids[c] * row_bytes;
     const float *qp = q + 4 * lane;
 
     if constexpr (NV > 0) {

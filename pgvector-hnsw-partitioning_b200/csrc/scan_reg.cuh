@@ -33,6 +33,15 @@ template <int R> struct RegW {
     uint32_t id[R];
     int L;          // warp-uniform
     float f;        // distance of entry ef-1 while L >= ef (warp-uniform)
+    // Invariant: slots >= L hold (+inf, 0xffffffff) -- "further than anything, already expanded" -- so that neither the
+    // position count, nor the search for the next unexpanded entry, nor the tie-run count needs an s < L test.
+    __device__ __forceinline__ void reset()
+    {
+        L = 0;
+        f = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; r++) { d[r] = __int_as_float(0x7f800000); id[r] = 0xffffffffu; }
+    }
 
     // this lane's entry r = j mod R, as a tree of two-way selects (a chain of compares is turned into an indexed
     // load by the compiler, which sends the whole list to local memory)
@@ -54,15 +63,16 @@ template <int R> struct RegW {
     __device__ __forceinline__ void refresh_f(int ef) { if (L >= ef) f = get_d(ef - 1); }
 
     // insert (ed, eid) keeping (distance, id) order, then trim to ef + the run of entries tying with entry ef-1
-    __device__ __forceinline__ int insert(float ed, uint32_t eid, int ef, int lane, int &low)
+    __device__ __forceinline__ int insert(float ed, uint32_t eid, int ef, int lane)
     {
         if (L + 1 > CAP) return ST_TAIL;
         int pos = 0;
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int s = lane * R + r;
-            const bool lt = s < L && (d[r] < ed || (d[r] == ed && (id[r] & ID_MASK) < eid));
+            const bool lt = d[r] < ed || (d[r] == ed && (id[r] & ID_MASK) < eid);
             pos += __popc(__ballot_sync(FULL, lt));
+            (void) s;
         }
         const float pd = __shfl_up_sync(FULL, d[R - 1], 1);
         const uint32_t pi = __shfl_up_sync(FULL, id[R - 1], 1);
@@ -82,12 +92,16 @@ template <int R> struct RegW {
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     const int s = lane * R + r;
-                    keep += __popc(__ballot_sync(FULL, s >= ef && s < L && d[r] == f));
+                    keep += __popc(__ballot_sync(FULL, s >= ef && d[r] == f));
+                }
+                if (ef + keep < L) {             // something fell off the end: restore the invariant
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+                        if (lane * R + r >= ef + keep) { d[r] = __int_as_float(0x7f800000); id[r] = 0xffffffffu; }
                 }
                 L = ef + keep;
             }
         }
-        if (pos < low) low = pos;
         return ST_OK;
     }
 };
@@ -96,7 +110,12 @@ template <int R> struct RegW {
 template <int R, typename VS>
 __device__ __forceinline__ int regw_as_entry(RegW<R> &w, VS &vs, int ef, int lane)
 {
-    if (w.L > 1) w.L = 1;
+    if (w.L > 1) {
+        w.L = 1;
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            if (lane * R + r >= 1) { w.d[r] = __int_as_float(0x7f800000); w.id[r] = 0xffffffffu; }
+    }
     vs.clear(lane);
     if (!vs.room(w.L)) return ST_TABLE;
     const bool sp = vs.spill(w.L);
@@ -149,14 +168,12 @@ __device__ __forceinline__ int search_layer_reg(const GraphView &g, RegW<R> &w, 
 {
     const int deg = lc == 0 ? 2 * g.m : g.m;
     const unsigned lt_mask = lanemask_lt();
-    int low = 0;
     for (;;) {
         // nearest unexpanded entry: slots are lane-major, so the lowest lane that has one has the lowest slot
         int mys = 0x7fffffff;
 #pragma unroll
         for (int r = R - 1; r >= 0; r--) {
-            const int s = lane * R + r;
-            if (s >= low && s < w.L && !(w.id[r] & EXP_BIT)) mys = s;
+            if (!(w.id[r] & EXP_BIT)) mys = lane * R + r;       // expanded entries and free slots carry the bit
         }
         const unsigned b = __ballot_sync(FULL, mys != 0x7fffffff);
         if (!b) break;
@@ -174,7 +191,6 @@ __device__ __forceinline__ int search_layer_reg(const GraphView &g, RegW<R> &w, 
         }
 #pragma unroll
         for (int r = 0; r < R; r++) if (lane * R + r == idx) w.id[r] |= EXP_BIT;
-        low = idx + 1;
         if (lc == 0) ctr.n_hop0++; else ctr.n_hopu++;
         if (!vs.room(deg)) return ST_TABLE;
         const int32_t *list = lc == 0 ? g.nbr0 + (size_t) cid * deg : g.nbru + ((size_t) g.uoff[cid] + (lc - 1)) * g.m;
@@ -202,7 +218,7 @@ __device__ __forceinline__ int search_layer_reg(const GraphView &g, RegW<R> &w, 
                 const float ed = __shfl_sync(FULL, myd, s);
                 const uint32_t eid = __shfl_sync(FULL, cj, s);
                 if (w.L >= ef && !(ed < w.f)) continue;
-                const int st = w.insert(ed, eid, ef, lane, low);
+                const int st = w.insert(ed, eid, ef, lane);
                 if (st) return st;
             }
         }
@@ -242,10 +258,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, MINB) scan_reg_kernel(const S
 
         QueryCounters ctr = { 0, 0, 0 };
         int st = ST_OK;
-        w.L = 0;
-        w.f = 0.f;
-#pragma unroll
-        for (int r = 0; r < R; r++) { w.d[r] = 0.f; w.id[r] = 0u; }
+        w.reset();
         if (g.entry >= 0) {
             const float d0 = one_distance<T, IP, NV>(g, q, g.entry, lane);
             ctr.n_dist = 1;

@@ -48,20 +48,18 @@ struct WList {               // sorted (distance, id) array; warp-uniform bookke
 // ---- visited sets ---------------------------------------------------------------------------
 struct VisitedHash {         // shared-memory table + per-warp overflow table in HBM (both exact)
     uint32_t *tab;           // shared memory, open addressing, linear probing
-    int slots, shift, count, limit;
+    int slots, count, limit; // any multiple of 4 slots: the home slot is mulhi(hash, slots), not a mask
     uint32_t *otab;          // overflow: used only once the shared table reached its load limit
-    int oslots, oshift, ocount, olimit;
+    int oslots, ocount, olimit;
     bool odirty;
     __device__ __forceinline__ void configure(int s)
     {
         slots = s;
-        shift = 32 - (31 - __clz(s));
         limit = s - (s >> 2);             // 75 % load
     }
     __device__ __forceinline__ void set_overflow(uint32_t *t, int s)
     {
         otab = t; oslots = s; odirty = true;   // first clear() wipes it
-        oshift = s > 1 ? 32 - (31 - __clz(s)) : 32;
         olimit = s - (s >> 2);
         ocount = 0;
     }
@@ -89,7 +87,7 @@ struct VisitedHash {         // shared-memory table + per-warp overflow table in
     // table, so a key lives in exactly one of the two tables)
     __device__ __forceinline__ bool spill(int incoming) const { return ocount > 0 || count + incoming > limit; }
 
-    __device__ __forceinline__ static bool probe_insert(uint32_t *t, uint32_t mask, uint32_t h, uint32_t key)
+    __device__ __forceinline__ static bool probe_insert(uint32_t *t, uint32_t nslots, uint32_t h, uint32_t key)
     {
         // most probes find the key already present (neighbour lists overlap heavily): a plain
         // load answers those; only an empty slot needs the CAS.  Slots only ever go EMPTY -> key.
@@ -101,17 +99,17 @@ struct VisitedHash {         // shared-memory table + per-warp overflow table in
                 if (old == EMPTY) return true;
                 if (old == key) return false;
             }
-            h = (h + 1) & mask;
+            h = h + 1 == nslots ? 0u : h + 1;
         }
     }
     __device__ __forceinline__ bool contains(uint32_t key) const
     {
-        uint32_t h = (key * 0x9E3779B1u) >> shift;
+        uint32_t h = __umulhi(key * 0x9E3779B1u, (uint32_t) slots);
         for (;;) {
             const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(tab + h);
             if (cur == key) return true;
             if (cur == EMPTY) return false;
-            h = (h + 1) & (slots - 1);
+            h = h + 1 == (uint32_t) slots ? 0u : h + 1;
         }
     }
     // insert one key; `to_overflow` is the warp-uniform decision of spill() for this batch.
@@ -119,9 +117,9 @@ struct VisitedHash {         // shared-memory table + per-warp overflow table in
     __device__ __forceinline__ bool insert(uint32_t key, bool to_overflow)
     {
         const uint32_t hk = key * 0x9E3779B1u;
-        if (!to_overflow) return probe_insert(tab, slots - 1, hk >> shift, key);
+        if (!to_overflow) return probe_insert(tab, (uint32_t) slots, __umulhi(hk, (uint32_t) slots), key);
         if (contains(key)) return false;
-        return probe_insert(otab, oslots - 1, oshift >= 32 ? 0u : hk >> oshift, key);
+        return probe_insert(otab, (uint32_t) oslots, __umulhi(hk, (uint32_t) oslots), key);
     }
     // account for `n_new` keys inserted by the last batch
     __device__ __forceinline__ void added(int n_new, bool to_overflow)
