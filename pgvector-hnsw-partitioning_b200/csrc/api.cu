@@ -334,7 +334,7 @@ int hb_set_option(hb_index *ix, const char *name, int value)
     else if (!strcmp(name, "fused_select")) ix->opt_fused_select = value;
     else if (!strcmp(name, "eval_table")) ix->opt_eval_table = value;
     else if (!strcmp(name, "build_fraction")) ix->opt_build_fraction = value > 0 ? value : 16;
-    else if (!strcmp(name, "build_fraction_small")) ix->opt_build_fraction_small = value > 0 ? value : 16;
+    else if (!strcmp(name, "build_fraction_small")) ix->opt_build_fraction_small = value > 0 ? value : 0;
     else if (!strcmp(name, "auto_grow")) ix->opt_auto_grow = value;
     else if (!strcmp(name, "vacuum_batch")) ix->opt_vacuum_batch = value;
     else { set_error("hb_set_option: unknown option %s", name); return HB_EINVAL; }

@@ -447,11 +447,15 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         return HB_OK;
     };
 
+    const int64_t final_size = ix->n + (int64_t) todo.size();
     while (pos < todo.size()) {
         const double t0 = now();
         n_batches++;
         const int64_t cur = ix->n;
-        const int frac = cur < 65536 ? std::max(2, ix->opt_build_fraction_small) : std::max(2, ix->opt_build_fraction);
+        // the latency-bound start-up: while the graph is small a batch may be 1/8 of it when the whole build stays small (recall of
+        // such graphs is insensitive to it: profiles/r2_experiments.md), 1/16 otherwise
+        const int frac_small = ix->opt_build_fraction_small > 0 ? ix->opt_build_fraction_small : (final_size < 262144 ? 8 : ix->opt_build_fraction);
+        const int frac = cur < 65536 ? std::max(2, frac_small) : std::max(2, ix->opt_build_fraction);
         int64_t b = std::max<int64_t>(1, std::min<int64_t>(auto_batch && cur < 524288 ? 8192 : max_batch, cur / frac));
         b = std::min<int64_t>(b, (int64_t) todo.size() - pos);
         levels.resize(b);
@@ -736,7 +740,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         if (trace) cudaEventRecord(tev[4], s);
         HB_CK(cudaMemcpyAsync(ix->h_flag, d_flag, 12, cudaMemcpyDeviceToHost, s));
         // while the device works on this batch: the rows of the next one (at most ~cur/16 + a chunk ahead)
-        rc = upload_upto((int64_t) pos + b + std::min<int64_t>(max_batch, (cur + b) / std::max(2, std::min(ix->opt_build_fraction, ix->opt_build_fraction_small)) + 1));
+        rc = upload_upto((int64_t) pos + b + std::min<int64_t>(max_batch, (cur + b) / 8 + 1));
         if (rc) return rc;
         const double t1 = now();
         HB_CK(cudaStreamSynchronize(s));

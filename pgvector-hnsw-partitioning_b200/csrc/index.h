@@ -105,7 +105,7 @@ struct hb_index {
     int opt_pair_cache = 1, opt_pair_fill = 1, opt_fused_select = 1, opt_eval_table = 1;
     int opt_auto_grow = 1;         // inserts beyond the capacity grow the index (hb_index_reserve) instead of failing
     int opt_build_fraction = 16;   // a batch is at most 1/opt_build_fraction of the graph
-    int opt_build_fraction_small = 16;   // the same while the graph holds fewer than 65536 elements (the latency-bound start-up)
+    int opt_build_fraction_small = 0;    // the same while the graph holds fewer than 65536 elements (the latency-bound start-up); 0 = automatic
     int opt_vacuum_batch = 0;      // elements repaired concurrently by hb_vacuum_repair (0 = 2048, 1 = one after the other)
     int opt_link_kernel = 0;       // 0 automatic, 1 warp-per-segment, 2 CTA-per-segment (link_kernel.cuh)
 

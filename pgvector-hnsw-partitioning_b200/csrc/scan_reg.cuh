@@ -131,8 +131,9 @@ __device__ __forceinline__ int regw_as_entry(RegW<R> &w, VS &vs, int ef, int lan
 
 // distances of the nnew candidates whose ids sit in cbuf[0 .. nnew) (shared memory, 16-byte aligned); lane j
 // (j < nnew) receives candidate j's distance, other lanes +inf
-template <typename T, int IP, int NV, int G>
-__device__ __forceinline__ float eval_compact(const GraphView &g, const float *q, const int32_t *cbuf, int nnew, int lane)
+template <typename T, int IP, int NV, int G, typename Hook = NoHook>
+__device__ __forceinline__ float eval_compact(const GraphView &g, const float *q, const int32_t *cbuf, int nnew, int lane,
+                                              Hook &&hook = Hook())
 {
     float myd = __int_as_float(0x7f800000);
     int g0 = 0;
@@ -149,7 +150,7 @@ __device__ __forceinline__ float eval_compact(const GraphView &g, const float *q
             const int2 v = *reinterpret_cast<const int2 *>(cbuf + g0);                             \
             ids[0] = v.x; ids[1] = v.y;                                                            \
         } else ids[0] = cbuf[g0];                                                                  \
-        const float s = group_distance<T, IP, NV, GG>(g.vecs, (uint32_t) g.row_bytes, g.nvec, q, ids, lane); \
+        const float s = group_distance<T, IP, NV, GG>(g.vecs, (uint32_t) g.row_bytes, g.nvec, q, ids, lane, hook, g0 == 0); \
         const float v = __shfl_sync(FULL, s, ((lane - g0) * (32 / GG)) & 31);                      \
         if (lane >= g0 && lane < g0 + GG) myd = v;                                                 \
         g0 += GG;                                                                                  \
@@ -162,12 +163,20 @@ __device__ __forceinline__ float eval_compact(const GraphView &g, const float *q
     return myd;
 }
 
+// Looking one expansion ahead (layer 0, lists of at most 32 neighbours): while the rows of the candidate being
+// expanded are in flight, the neighbour list of the NEXT nearest unexpanded candidate -- loaded into registers at the
+// start of the hop -- is filtered through the visited table (read only) and the rows that would be evaluated next are
+// asked into L2.  Nothing else changes: if that candidate is indeed expanded next (the usual case once the search has
+// reached the query's neighbourhood), its list is already in registers and its rows come from L2 instead of HBM;
+// if not, the prefetch was wasted.  Results, counters and expansion order are untouched.
 template <typename T, int IP, int NV, int G, int R, typename VS>
 __device__ __forceinline__ int search_layer_reg(const GraphView &g, RegW<R> &w, VS &vs, const float *q, int32_t *cbuf, int ef,
-                                                int lc, int lane, QueryCounters &ctr)
+                                                int lc, int lane, QueryCounters &ctr, bool look = true)
 {
     const int deg = lc == 0 ? 2 * g.m : g.m;
     const unsigned lt_mask = lanemask_lt();
+    const bool ahead = look && lc == 0 && deg <= 32;
+    int32_t spec_c = -1, nb_spec = -1;           // candidate whose list sits in nb_spec (one neighbour per lane)
     for (;;) {
         // nearest unexpanded entry: slots are lane-major, so the lowest lane that has one has the lowest slot
         int mys = 0x7fffffff;
@@ -181,22 +190,35 @@ __device__ __forceinline__ int search_layer_reg(const GraphView &g, RegW<R> &w, 
         const int idx = __shfl_sync(FULL, mys, src);
         const uint32_t mine = RegW<R>::pick(w.id, mys);
         const uint32_t cid = __shfl_sync(FULL, mine, src);
-        if (lc == 0) {
-            // the candidate after this one is the likeliest next expansion: start its neighbour list towards L2
+        const int32_t *list = lc == 0 ? g.nbr0 + (size_t) cid * deg : g.nbru + ((size_t) g.uoff[cid] + (lc - 1)) * g.m;
+        // this candidate's list: already here when the look-ahead guessed right
+        int32_t nb0 = -1;
+        if (ahead && (int32_t) cid == spec_c) nb0 = nb_spec;
+        else if (lane < deg) nb0 = list[lane];
+        // the candidate after this one is the likeliest next expansion: fetch its list now
+        int32_t next_c = -1, nb_next = -1;
+        if (ahead) {
             const unsigned b2 = b & (b - 1);
             if (b2) {
-                const uint32_t nid = __shfl_sync(FULL, mine, __ffs(b2) - 1) & ID_MASK;
-                if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.nbr0 + (size_t) nid * deg));
+                next_c = (int32_t) (__shfl_sync(FULL, mine, __ffs(b2) - 1) & ID_MASK);
+                if (lane < deg) nb_next = __ldg(g.nbr0 + (size_t) next_c * deg + lane);
             }
         }
+        bool looked = false;
+        auto look_ahead = [&](bool run) {
+            if (!run || looked) return;
+            looked = true;
+            if (next_c < 0) return;
+            if (nb_next >= 0 && !vs.contains((uint32_t) nb_next))
+                prefetch_l2_bulk(g.vecs + (size_t) nb_next * g.row_bytes, (uint32_t) g.row_bytes);
+        };
 #pragma unroll
         for (int r = 0; r < R; r++) if (lane * R + r == idx) w.id[r] |= EXP_BIT;
         if (lc == 0) ctr.n_hop0++; else ctr.n_hopu++;
         if (!vs.room(deg)) return ST_TABLE;
-        const int32_t *list = lc == 0 ? g.nbr0 + (size_t) cid * deg : g.nbru + ((size_t) g.uoff[cid] + (lc - 1)) * g.m;
         for (int cb = 0; cb < deg; cb += 32) {
             const int i = cb + lane;
-            const int32_t nb = i < deg ? list[i] : -1;
+            const int32_t nb = cb == 0 ? nb0 : (i < deg ? list[i] : -1);
             const bool sp = vs.spill(min(32, deg - cb));
             bool isnew = false;
             if (nb >= 0) isnew = vs.insert((uint32_t) nb, sp);
@@ -209,7 +231,7 @@ __device__ __forceinline__ int search_layer_reg(const GraphView &g, RegW<R> &w, 
             if (isnew) cbuf[__popc(nmask & lt_mask)] = nb;
             __syncwarp();
             const uint32_t cj = lane < nnew ? (uint32_t) cbuf[lane] : 0u;
-            const float myd = eval_compact<T, IP, NV, G>(g, q, cbuf, nnew, lane);
+            const float myd = eval_compact<T, IP, NV, G>(g, q, cbuf, nnew, lane, look_ahead);
             __syncwarp();
             unsigned amask = __ballot_sync(FULL, lane < nnew && (w.L < ef || myd < w.f));
             while (amask) {
@@ -221,6 +243,11 @@ __device__ __forceinline__ int search_layer_reg(const GraphView &g, RegW<R> &w, 
                 const int st = w.insert(ed, eid, ef, lane);
                 if (st) return st;
             }
+        }
+        if (ahead) {
+            look_ahead(true);                    // a hop without new candidates still looks ahead
+            spec_c = next_c;
+            nb_spec = nb_next;
         }
     }
     return ST_OK;
@@ -272,7 +299,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, MINB) scan_reg_kernel(const S
             if (st == ST_OK) {
                 vs.configure(p.slots);
                 st = regw_as_entry(w, vs, ef, lane);
-                if (st == ST_OK) st = search_layer_reg<T, IP, NV, G, R>(g, w, vs, q, cbuf, ef, 0, lane, ctr);
+                if (st == ST_OK) st = search_layer_reg<T, IP, NV, G, R>(g, w, vs, q, cbuf, ef, 0, lane, ctr, p.variant != 7);
             }
         }
         if (st != ST_OK) {
