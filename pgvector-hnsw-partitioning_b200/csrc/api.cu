@@ -633,6 +633,17 @@ static int scan_dev(hb_index *ix, ScanWs &ws, const void *dev_queries, int64_t n
     p.ef = ef;
     p.capW = ((std::max(ef, nep) + 16 + 3) / 4) * 4;
     p.slots = choose_slots(ix, ef, p.capW);
+    const int regR = reg_list_R(ix->nvec, ef, dev_ep, ix->opt_variant);
+    if (regR && ix->opt_slots <= 0) {
+        // register-list kernel, one warp per CTA: the visited table is what fills shared memory.  Size it so that 24
+        // (128-d) / 16 (256-d) one-warp CTAs are resident per SM (each CTA also costs 1 kB of reserved shared memory)
+        const int warps = ix->nvec <= 32 ? 24 : 16;
+        const size_t per_cta = (size_t) 233472 / warps - 1024;
+        const size_t fixed = (size_t) ix->nvec * (ix->dtype == HB_F32 ? 4 : 8) * 4 + 128 + 16;
+        int sl = (int) ((per_cta - fixed) / 4) & ~15;
+        sl = std::min(sl, pow2ceil(ef * 64));
+        if (sl >= 256) p.slots = sl;
+    }
     p.upper_slots = std::min(p.slots, 1024);
     p.out_elem = out_elem; p.out_dist = out_dist; p.out_cnt = out_cnt;
     p.out_stride = std::max(ef, nep);
@@ -675,11 +686,12 @@ static int scan_dev(hb_index *ix, ScanWs &ws, const void *dev_queries, int64_t n
         int os = HB_OVERFLOW_SLOTS;
         while (os < ef * 64 && os < 32768) os <<= 1;
         p.oslots = os;
-        // (the register-list kernel needs a little less shared memory per CTA than this: size for the smaller)
-        const size_t cta_smem = (scan_warp_smem_bytes(ix, p.capW, p.slots) - (size_t) p.capW * 8) * SCAN_WARPS;
-        int ctas = (int) std::min<size_t>(MAX_CTAS_PER_SM, (227 * 1024) / std::max<size_t>(cta_smem, 1));
-        if (ctas < 1) ctas = 1;
-        HB_CK(ws.ovf.ensure(sizeof(uint32_t) * (size_t) ix->num_sms * ctas * SCAN_WARPS * p.oslots));
+        // one slice per warp that can be resident: an upper bound from the smaller of the two kernels' per-warp
+        // shared memory (the launchers clamp their grids to MAX_CTAS_PER_SM * SCAN_WARPS warps per SM)
+        const size_t warp_smem = scan_warp_smem_bytes(ix, p.capW, p.slots) - (size_t) p.capW * 8;
+        int warps = (int) std::min<size_t>((size_t) MAX_CTAS_PER_SM * SCAN_WARPS, (228 * 1024) / std::max<size_t>(warp_smem, 1));
+        if (warps < SCAN_WARPS) warps = SCAN_WARPS;
+        HB_CK(ws.ovf.ensure(sizeof(uint32_t) * (size_t) ix->num_sms * warps * p.oslots));
     }
     p.ovf = ws.ovf.as<uint32_t>();
 
@@ -687,7 +699,6 @@ static int scan_dev(hb_index *ix, ScanWs &ws, const void *dev_queries, int64_t n
     HB_CK(cudaEventRecord(ws.ev0, s));
     p.work = misc + 0;
     ScanLaunchInfo info;
-    const int regR = reg_list_R(ix->nvec, ef, dev_ep, ix->opt_variant);
     if (regR) HB_CK(get_scan_reg_launcher(ix->dtype, ip)(p, regR, ix->num_sms, ix->opt_grid, s, &info));
     else HB_CK(get_scan_launcher(ix->dtype, ip, false)(p, ix->num_sms, ix->opt_grid, s, &info));
     // queries whose tie tail (or overflow table) outgrew the fast path run again with a bitmap in HBM

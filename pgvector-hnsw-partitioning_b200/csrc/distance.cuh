@@ -128,13 +128,10 @@ template <int VEC> __device__ __forceinline__ float fold_lane2(const f32x2 (&p)[
 // NV > 0: the row is exactly 32*NV chunks (every lane owns NV chunks; loads are issued
 // back-to-back from one base pointer per row with immediate offsets, G*NV 128-bit loads in flight
 // per lane); NV == 0: run-time loop for any row length.
-// `hook(run)` is called once the loads of the rows are issued and before they are consumed: work placed there
-// overlaps the rows' flight time (scan_reg.cuh uses it to look one expansion ahead).
-struct NoHook { __device__ __forceinline__ void operator()(bool) const {} };
-template <typename T, int IP, int NV, int G, typename Hook = NoHook>
+template <typename T, int IP, int NV, int G>
 __device__ __forceinline__ void group_partials(const char *__restrict__ vecs, uint32_t row_bytes, int nvec,
                                                const float *q, const int32_t (&ids)[G], int lane,
-                                               float (&part)[G], Hook &&hook = Hook(), bool run_hook = false)
+                                               float (&part)[G])
 {
     constexpr int VEC = Vec<T>::VEC;
     constexpr bool HALF = sizeof(T) == 2;
@@ -156,7 +153,6 @@ __device__ __forceinline__ void group_partials(const char *__restrict__ vecs, ui
         for (int c = 0; c < G; c++)
 #pragma unroll
             for (int j = 0; j < NV; j++) raw[c][j] = ldg_stream(rp[c] + 512 * j);
-        hook(run_hook);
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             const float4 qa = *reinterpret_cast<const float4 *>(qp + 128 * j);
@@ -166,7 +162,6 @@ __device__ __forceinline__ void group_partials(const char *__restrict__ vecs, ui
             for (int c = 0; c < G; c++) accum_chunk<T, IP>(acc[c], raw[c][j], qa, qb);
         }
     } else {
-        hook(run_hook);
         const int plane = 4 * nvec;
         for (int ch = lane; ch < nvec; ch += 32) {
             uint4 raw[G];
@@ -211,13 +206,12 @@ template <> struct XReduce<1> {
 };
 
 // distances of G candidates; result of candidate c is returned in every lane via out[c]
-template <typename T, int IP, int NV, int G, typename Hook = NoHook>
+template <typename T, int IP, int NV, int G>
 __device__ __forceinline__ float group_distance(const char *__restrict__ vecs, uint32_t row_bytes, int nvec,
-                                                const float *q, const int32_t (&ids)[G], int lane, Hook &&hook = Hook(),
-                                                bool run_hook = false)
+                                                const float *q, const int32_t (&ids)[G], int lane)
 {
     float part[G];
-    group_partials<T, IP, NV, G>(vecs, row_bytes, nvec, q, ids, lane, part, hook, run_hook);
+    group_partials<T, IP, NV, G>(vecs, row_bytes, nvec, q, ids, lane, part);
     const float s = XReduce<G>::run(part, lane, 16);
     return IP == 1 ? -s : s;   // lane (c * 32/G) .. hold candidate c
 }

@@ -131,9 +131,8 @@ __device__ __forceinline__ int regw_as_entry(RegW<R> &w, VS &vs, int ef, int lan
 
 // distances of the nnew candidates whose ids sit in cbuf[0 .. nnew) (shared memory, 16-byte aligned); lane j
 // (j < nnew) receives candidate j's distance, other lanes +inf
-template <typename T, int IP, int NV, int G, typename Hook = NoHook>
-__device__ __forceinline__ float eval_compact(const GraphView &g, const float *q, const int32_t *cbuf, int nnew, int lane,
-                                              Hook &&hook = Hook())
+template <typename T, int IP, int NV, int G>
+__device__ __forceinline__ float eval_compact(const GraphView &g, const float *q, const int32_t *cbuf, int nnew, int lane)
 {
     float myd = __int_as_float(0x7f800000);
     int g0 = 0;
@@ -150,7 +149,7 @@ __device__ __forceinline__ float eval_compact(const GraphView &g, const float *q
             const int2 v = *reinterpret_cast<const int2 *>(cbuf + g0);                             \
             ids[0] = v.x; ids[1] = v.y;                                                            \
         } else ids[0] = cbuf[g0];                                                                  \
-        const float s = group_distance<T, IP, NV, GG>(g.vecs, (uint32_t) g.row_bytes, g.nvec, q, ids, lane, hook, g0 == 0); \
+        const float s = group_distance<T, IP, NV, GG>(g.vecs, (uint32_t) g.row_bytes, g.nvec, q, ids, lane); \
         const float v = __shfl_sync(FULL, s, ((lane - g0) * (32 / GG)) & 31);                      \
         if (lane >= g0 && lane < g0 + GG) myd = v;                                                 \
         g0 += GG;                                                                                  \
@@ -163,20 +162,12 @@ __device__ __forceinline__ float eval_compact(const GraphView &g, const float *q
     return myd;
 }
 
-// Looking one expansion ahead (layer 0, lists of at most 32 neighbours): while the rows of the candidate being
-// expanded are in flight, the neighbour list of the NEXT nearest unexpanded candidate -- loaded into registers at the
-// start of the hop -- is filtered through the visited table (read only) and the rows that would be evaluated next are
-// asked into L2.  Nothing else changes: if that candidate is indeed expanded next (the usual case once the search has
-// reached the query's neighbourhood), its list is already in registers and its rows come from L2 instead of HBM;
-// if not, the prefetch was wasted.  Results, counters and expansion order are untouched.
 template <typename T, int IP, int NV, int G, int R, typename VS>
 __device__ __forceinline__ int search_layer_reg(const GraphView &g, RegW<R> &w, VS &vs, const float *q, int32_t *cbuf, int ef,
-                                                int lc, int lane, QueryCounters &ctr, bool look = true)
+                                                int lc, int lane, QueryCounters &ctr)
 {
     const int deg = lc == 0 ? 2 * g.m : g.m;
     const unsigned lt_mask = lanemask_lt();
-    const bool ahead = look && lc == 0 && deg <= 32;
-    int32_t spec_c = -1, nb_spec = -1;           // candidate whose list sits in nb_spec (one neighbour per lane)
     for (;;) {
         // nearest unexpanded entry: slots are lane-major, so the lowest lane that has one has the lowest slot
         int mys = 0x7fffffff;
@@ -188,37 +179,15 @@ __device__ __forceinline__ int search_layer_reg(const GraphView &g, RegW<R> &w, 
         if (!b) break;
         const int src = __ffs(b) - 1;
         const int idx = __shfl_sync(FULL, mys, src);
-        const uint32_t mine = RegW<R>::pick(w.id, mys);
-        const uint32_t cid = __shfl_sync(FULL, mine, src);
-        const int32_t *list = lc == 0 ? g.nbr0 + (size_t) cid * deg : g.nbru + ((size_t) g.uoff[cid] + (lc - 1)) * g.m;
-        // this candidate's list: already here when the look-ahead guessed right
-        int32_t nb0 = -1;
-        if (ahead && (int32_t) cid == spec_c) nb0 = nb_spec;
-        else if (lane < deg) nb0 = list[lane];
-        // the candidate after this one is the likeliest next expansion: fetch its list now
-        int32_t next_c = -1, nb_next = -1;
-        if (ahead) {
-            const unsigned b2 = b & (b - 1);
-            if (b2) {
-                next_c = (int32_t) (__shfl_sync(FULL, mine, __ffs(b2) - 1) & ID_MASK);
-                if (lane < deg) nb_next = __ldg(g.nbr0 + (size_t) next_c * deg + lane);
-            }
-        }
-        bool looked = false;
-        auto look_ahead = [&](bool run) {
-            if (!run || looked) return;
-            looked = true;
-            if (next_c < 0) return;
-            if (nb_next >= 0 && !vs.contains((uint32_t) nb_next))
-                prefetch_l2_bulk(g.vecs + (size_t) nb_next * g.row_bytes, (uint32_t) g.row_bytes);
-        };
+        const uint32_t cid = __shfl_sync(FULL, RegW<R>::pick(w.id, mys), src);
 #pragma unroll
         for (int r = 0; r < R; r++) if (lane * R + r == idx) w.id[r] |= EXP_BIT;
         if (lc == 0) ctr.n_hop0++; else ctr.n_hopu++;
         if (!vs.room(deg)) return ST_TABLE;
+        const int32_t *list = lc == 0 ? g.nbr0 + (size_t) cid * deg : g.nbru + ((size_t) g.uoff[cid] + (lc - 1)) * g.m;
         for (int cb = 0; cb < deg; cb += 32) {
             const int i = cb + lane;
-            const int32_t nb = cb == 0 ? nb0 : (i < deg ? list[i] : -1);
+            const int32_t nb = i < deg ? list[i] : -1;
             const bool sp = vs.spill(min(32, deg - cb));
             bool isnew = false;
             if (nb >= 0) isnew = vs.insert((uint32_t) nb, sp);
@@ -231,7 +200,7 @@ __device__ __forceinline__ int search_layer_reg(const GraphView &g, RegW<R> &w, 
             if (isnew) cbuf[__popc(nmask & lt_mask)] = nb;
             __syncwarp();
             const uint32_t cj = lane < nnew ? (uint32_t) cbuf[lane] : 0u;
-            const float myd = eval_compact<T, IP, NV, G>(g, q, cbuf, nnew, lane, look_ahead);
+            const float myd = eval_compact<T, IP, NV, G>(g, q, cbuf, nnew, lane);
             __syncwarp();
             unsigned amask = __ballot_sync(FULL, lane < nnew && (w.L < ef || myd < w.f));
             while (amask) {
@@ -244,11 +213,6 @@ __device__ __forceinline__ int search_layer_reg(const GraphView &g, RegW<R> &w, 
                 if (st) return st;
             }
         }
-        if (ahead) {
-            look_ahead(true);                    // a hop without new candidates still looks ahead
-            spec_c = next_c;
-            nb_spec = nb_next;
-        }
     }
     return ST_OK;
 }
@@ -258,8 +222,11 @@ template <typename T> __host__ __device__ inline size_t scan_reg_warp_smem(int n
     return (((size_t) nvec * Vec<T>::VEC * 4 + (size_t) slots * 4 + 128) + 15) & ~(size_t) 15;
 }
 
-template <typename T, int IP, int NV, int G, int R, int MINB>
-__global__ void __launch_bounds__(SCAN_WARPS * 32, MINB) scan_reg_kernel(const ScanParams p)
+// WPB warps (= concurrent queries) per CTA.  One warp per CTA by default: a CTA's resources come back the moment its
+// last query is done, so the tail of one batch overlaps the start of the next at warp granularity (with four warps per
+// CTA three idle warps wait for the straggler; measured in profiles/r2_experiments.md).
+template <typename T, int IP, int NV, int G, int R, int MINB, int WPB>
+__global__ void __launch_bounds__(WPB * 32, MINB) scan_reg_kernel(const ScanParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -269,7 +236,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, MINB) scan_reg_kernel(const S
     int32_t *cbuf = reinterpret_cast<int32_t *>(base + (size_t) g.nvec * Vec<T>::VEC * 4);
     VisitedHash vs;
     vs.tab = reinterpret_cast<uint32_t *>(cbuf + 32);
-    vs.set_overflow(p.ovf + ((size_t) blockIdx.x * SCAN_WARPS + warp) * p.oslots, p.oslots);
+    vs.set_overflow(p.ovf + ((size_t) blockIdx.x * WPB + warp) * p.oslots, p.oslots);
     RegW<R> w;
     const int ef = p.ef;
 
@@ -299,7 +266,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, MINB) scan_reg_kernel(const S
             if (st == ST_OK) {
                 vs.configure(p.slots);
                 st = regw_as_entry(w, vs, ef, lane);
-                if (st == ST_OK) st = search_layer_reg<T, IP, NV, G, R>(g, w, vs, q, cbuf, ef, 0, lane, ctr, p.variant != 7);
+                if (st == ST_OK) st = search_layer_reg<T, IP, NV, G, R>(g, w, vs, q, cbuf, ef, 0, lane, ctr);
             }
         }
         if (st != ST_OK) {
@@ -336,11 +303,11 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, MINB) scan_reg_kernel(const S
     }
 }
 
-template <typename T, int IP, int NV, int G, int R, int MINB>
+template <typename T, int IP, int NV, int G, int R, int MINB, int WPB>
 cudaError_t launch_scan_reg_variant(const ScanParams &p, int num_sms, int max_grid, cudaStream_t stream, ScanLaunchInfo *info)
 {
-    auto kern = scan_reg_kernel<T, IP, NV, G, R, MINB>;
-    const size_t smem = scan_reg_warp_smem<T>(p.g.nvec, p.slots) * SCAN_WARPS;
+    auto kern = scan_reg_kernel<T, IP, NV, G, R, MINB, WPB>;
+    const size_t smem = scan_reg_warp_smem<T>(p.g.nvec, p.slots) * WPB;
     static thread_local size_t seen_smem[16];
     static thread_local int seen_bps[16];
     int dev = 0;
@@ -351,18 +318,18 @@ cudaError_t launch_scan_reg_variant(const ScanParams &p, int num_sms, int max_gr
     else {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SCAN_WARPS * 32, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WPB * 32, smem);
         if (e != cudaSuccess) return e;
         if (bps < 1) return cudaErrorInvalidConfiguration;
         seen_smem[dev] = smem; seen_bps[dev] = bps;
     }
-    if (bps > MAX_CTAS_PER_SM) bps = MAX_CTAS_PER_SM;
-    const int64_t want = (p.nq + SCAN_WARPS - 1) / SCAN_WARPS;
+    if (bps * WPB > MAX_CTAS_PER_SM * SCAN_WARPS) bps = MAX_CTAS_PER_SM * SCAN_WARPS / WPB;     // the overflow tables are sized for this many warps
+    const int64_t want = (p.nq + WPB - 1) / WPB;
     int grid = (int) (want < (int64_t) bps * num_sms ? want : (int64_t) bps * num_sms);
     if (max_grid > 0 && grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
     if (info) { info->grid = grid; info->smem = smem; info->blocks_per_sm = bps; }
-    kern<<<grid, SCAN_WARPS * 32, smem, stream>>>(p);
+    kern<<<grid, WPB * 32, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -382,19 +349,18 @@ template <typename T, int IP>
 cudaError_t launch_scan_reg_t(const ScanParams &p, int R, int num_sms, int max_grid, cudaStream_t stream, ScanLaunchInfo *info)
 {
     const int nv = nv_of(p.g.nvec);
-    if (nv == 1 && R == 2 && p.variant) {       // occupancy experiments (hb_set_option "variant")
+    if (nv == 1 && R == 2 && p.variant) {       // experiments (hb_set_option "variant"): four warps per CTA, other occupancies
         switch (p.variant) {
-        case 1: return launch_scan_reg_variant<T, IP, 1, 8, 2, 8>(p, num_sms, max_grid, stream, info);
-        case 2: return launch_scan_reg_variant<T, IP, 1, 4, 2, 8>(p, num_sms, max_grid, stream, info);
-        case 3: return launch_scan_reg_variant<T, IP, 1, 4, 2, 10>(p, num_sms, max_grid, stream, info);
-        case 4: return launch_scan_reg_variant<T, IP, 1, 2, 2, 12>(p, num_sms, max_grid, stream, info);
+        case 1: return launch_scan_reg_variant<T, IP, 1, 8, 2, 6, 4>(p, num_sms, max_grid, stream, info);
+        case 2: return launch_scan_reg_variant<T, IP, 1, 4, 2, 32, 1>(p, num_sms, max_grid, stream, info);
+        case 3: return launch_scan_reg_variant<T, IP, 1, 8, 2, 8, 4>(p, num_sms, max_grid, stream, info);
         default: break;
         }
     }
-    if (nv == 1 && R == 2) return launch_scan_reg_variant<T, IP, 1, 8, 2, 6>(p, num_sms, max_grid, stream, info);
-    if (nv == 1 && R == 4) return launch_scan_reg_variant<T, IP, 1, 8, 4, 6>(p, num_sms, max_grid, stream, info);
-    if (nv == 2 && R == 2) return launch_scan_reg_variant<T, IP, 2, 8, 2, 4>(p, num_sms, max_grid, stream, info);
-    if (nv == 2 && R == 4) return launch_scan_reg_variant<T, IP, 2, 8, 4, 4>(p, num_sms, max_grid, stream, info);
+    if (nv == 1 && R == 2) return launch_scan_reg_variant<T, IP, 1, 8, 2, 24, 1>(p, num_sms, max_grid, stream, info);
+    if (nv == 1 && R == 4) return launch_scan_reg_variant<T, IP, 1, 8, 4, 24, 1>(p, num_sms, max_grid, stream, info);
+    if (nv == 2 && R == 2) return launch_scan_reg_variant<T, IP, 2, 8, 2, 16, 1>(p, num_sms, max_grid, stream, info);
+    if (nv == 2 && R == 4) return launch_scan_reg_variant<T, IP, 2, 8, 4, 16, 1>(p, num_sms, max_grid, stream, info);
     return cudaErrorInvalidConfiguration;
 }
 
