@@ -48,8 +48,11 @@ template <typename T> __host__ __device__ inline size_t scan_warp_smem(int nvec,
     return (b + 15) & ~(size_t) 15;
 }
 
-template <typename T, int IP, int NV, int G, bool SLOW, int MINB>
-__global__ void __launch_bounds__(SCAN_WARPS * 32, MINB) scan_kernel(const ScanParams p)
+// WPB warps (= concurrent queries) per CTA: one on the fast path, so that a CTA's resources come back the moment its
+// last query is done and the tail of one batch overlaps the start of the next at warp granularity; SCAN_WARPS on the
+// large-visited-set path, whose HBM scratch is sliced per CTA.
+template <typename T, int IP, int NV, int G, bool SLOW, int MINB, int WPB = (SLOW ? SCAN_WARPS : 1)>
+__global__ void __launch_bounds__(WPB * 32, MINB * (SCAN_WARPS / WPB)) scan_kernel(const ScanParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -62,7 +65,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, MINB) scan_kernel(const ScanP
     WList w;
     VS vs;
     if constexpr (SLOW) {
-        const size_t gw = (size_t) blockIdx.x * SCAN_WARPS + warp;
+        const size_t gw = (size_t) blockIdx.x * WPB + warp;
         vs.bits = p.gbits + gw * p.gwords;
         vs.words = p.gwords;
         w.d = p.gwd + gw * p.gcap;
@@ -71,7 +74,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32, MINB) scan_kernel(const ScanP
     } else {
         unsigned char *s = base + (size_t) g.nvec * Vec<T>::VEC * 4;
         vs.tab = reinterpret_cast<uint32_t *>(s);
-        vs.set_overflow(p.ovf + ((size_t) blockIdx.x * SCAN_WARPS + warp) * p.oslots, p.oslots);
+        vs.set_overflow(p.ovf + ((size_t) blockIdx.x * WPB + warp) * p.oslots, p.oslots);
         w.d = reinterpret_cast<float *>(s + (size_t) p.slots * 4);
         w.id = reinterpret_cast<uint32_t *>(s + (size_t) p.slots * 4 + (size_t) p.capW * 4);
         w.cap = p.capW;
@@ -166,8 +169,9 @@ template <typename T, int IP, int NV, int G, bool SLOW, int MINB>
 cudaError_t launch_scan_variant(const ScanParams &p, int num_sms, int max_grid, cudaStream_t stream,
                                 ScanLaunchInfo *info)
 {
-    auto kern = scan_kernel<T, IP, NV, G, SLOW, MINB>;
-    const size_t smem = scan_warp_smem<T>(p.g.nvec, p.capW, p.slots, SLOW) * SCAN_WARPS;
+    constexpr int WPB = SLOW ? SCAN_WARPS : 1;
+    auto kern = scan_kernel<T, IP, NV, G, SLOW, MINB, WPB>;
+    const size_t smem = scan_warp_smem<T>(p.g.nvec, p.capW, p.slots, SLOW) * WPB;
     // the function attribute and the occupancy query cost several microseconds each: remember them per
     // device for the shared-memory size last used (a single scan is only ~350 us long); per host thread,
     // so that handles driven from different threads never share mutable state
@@ -181,18 +185,18 @@ cudaError_t launch_scan_variant(const ScanParams &p, int num_sms, int max_grid, 
     else {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SCAN_WARPS * 32, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WPB * 32, smem);
         if (e != cudaSuccess) return e;
         if (bps < 1) return cudaErrorInvalidConfiguration;
         seen_smem[dev] = smem; seen_bps[dev] = bps;
     }
-    if (bps > MAX_CTAS_PER_SM) bps = MAX_CTAS_PER_SM;
-    int64_t want = SLOW ? max_grid : (p.nq + SCAN_WARPS - 1) / SCAN_WARPS;
+    if (bps * WPB > MAX_CTAS_PER_SM * SCAN_WARPS) bps = MAX_CTAS_PER_SM * SCAN_WARPS / WPB;     // the overflow tables are sized for this many warps
+    int64_t want = SLOW ? max_grid : (p.nq + WPB - 1) / WPB;
     int grid = (int) (want < (int64_t) bps * num_sms ? want : (int64_t) bps * num_sms);
     if (max_grid > 0 && grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
     if (info) { info->grid = grid; info->smem = smem; info->blocks_per_sm = bps; }
-    kern<<<grid, SCAN_WARPS * 32, smem, stream>>>(p);
+    kern<<<grid, WPB * 32, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
