@@ -48,10 +48,10 @@ template <typename T> __host__ __device__ inline size_t scan_warp_smem(int nvec,
     return (b + 15) & ~(size_t) 15;
 }
 
-// WPB warps (= concurrent queries) per CTA: one on the fast path, so that a CTA's resources come back the moment its
-// last query is done and the tail of one batch overlaps the start of the next at warp granularity; SCAN_WARPS on the
-// large-visited-set path, whose HBM scratch is sliced per CTA.
-template <typename T, int IP, int NV, int G, bool SLOW, int MINB, int WPB = (SLOW ? SCAN_WARPS : 1)>
+// WPB warps (= concurrent queries) per CTA.  SCAN_WARPS here: with rows of several kB one-warp CTAs measured 12 % slower
+// (3.56 vs 4.05 M queries/s at 1M x 768 in the same run), while the register-list kernel for short rows gains 5-9 % from
+// them (profiles/r2_experiments.md).
+template <typename T, int IP, int NV, int G, bool SLOW, int MINB, int WPB = SCAN_WARPS>
 __global__ void __launch_bounds__(WPB * 32, MINB * (SCAN_WARPS / WPB)) scan_kernel(const ScanParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -165,11 +165,10 @@ __global__ void __launch_bounds__(WPB * 32, MINB * (SCAN_WARPS / WPB)) scan_kern
 // host-side launch helper -------------------------------------------------------------------
 struct ScanLaunchInfo { int grid; size_t smem; int blocks_per_sm; };
 
-template <typename T, int IP, int NV, int G, bool SLOW, int MINB>
+template <typename T, int IP, int NV, int G, bool SLOW, int MINB, int WPB = SCAN_WARPS>
 cudaError_t launch_scan_variant(const ScanParams &p, int num_sms, int max_grid, cudaStream_t stream,
                                 ScanLaunchInfo *info)
 {
-    constexpr int WPB = SLOW ? SCAN_WARPS : 1;
     auto kern = scan_kernel<T, IP, NV, G, SLOW, MINB, WPB>;
     const size_t smem = scan_warp_smem<T>(p.g.nvec, p.capW, p.slots, SLOW) * WPB;
     // the function attribute and the occupancy query cost several microseconds each: remember them per
@@ -218,6 +217,7 @@ cudaError_t launch_scan_t(const ScanParams &p, int num_sms, int max_grid, cudaSt
     else {
         if (nv_of(p.g.nvec) == 6 && p.variant) {
             switch (p.variant) {
+            case 8: return launch_scan_variant<T, IP, 6, 4, false, 4, 1>(p, num_sms, max_grid, stream, info);      // one warp per CTA
             case 1: return launch_scan_variant<T, IP, 6, 4, false, 3>(p, num_sms, max_grid, stream, info);
             case 2: return launch_scan_variant<T, IP, 6, 2, false, 4>(p, num_sms, max_grid, stream, info);
             case 3: return launch_scan_variant<T, IP, 6, 2, false, 5>(p, num_sms, max_grid, stream, info);

@@ -27,6 +27,8 @@ c = ix.counters(reset=True)
 row = dim * (2 if half else 4)
 print("build %d x %d %s: %.2f s = %.0f vectors/s; n_dist %.0f/insert n_pair %.0f/insert; algorithmic %.0f GB/s" %
       (n, dim, opc, dt, n / dt, c["n_dist"] / n, c["n_pair"] / n, (c["n_dist"] + c["n_pair"]) * row / dt / 1e9), flush=True)
+if os.environ.get("HB_BUILD_ONLY"):
+    sys.exit(0)
 q = gen_set(1000, dim, 20260104 + 1000, dev)
 qh = (q.half() if half else q).cpu().numpy()
 gt, _, st = ix.bruteforce(qh, 10, stats=True)
