@@ -493,6 +493,16 @@ int hb_index_load(hb_index *ix, int64_t n, int64_t upper_rows, int32_t entry, co
         set_error("hb_index_load: graph (%lld elements, %lld upper rows) exceeds capacity", (long long) n, (long long) upper_rows);
         return HB_ENOMEM;
     }
+    if (n > 0 && (entry < 0 || entry >= n)) { set_error("hb_index_load: entry point %d is not an element (n = %lld)", entry, (long long) n); return HB_EINVAL; }
+    for (int64_t i = 0; i < n * 2 * ix->m; i++)
+        if (nbr0[i] < -1 || nbr0[i] >= n) { set_error("hb_index_load: layer-0 neighbour id %d out of range", nbr0[i]); return HB_EINVAL; }
+    for (int64_t i = 0; i < upper_rows * ix->m; i++)
+        if (nbru[i] < -1 || nbru[i] >= n) { set_error("hb_index_load: upper-layer neighbour id %d out of range", nbru[i]); return HB_EINVAL; }
+    for (int64_t e = 0; e < n; e++)
+        if (uoff[e] < -1 || (level[e] > 0 && (uoff[e] < 0 || (int64_t) uoff[e] + level[e] > upper_rows))) {
+            set_error("hb_index_load: element %lld: upper rows [%d, +%d) out of range", (long long) e, uoff[e], (int) level[e]);
+            return HB_EINVAL;
+        }
     HB_CK(cudaSetDevice(ix->device));
     int rc = upload_rows(ix, 0, vecs, n, 0);
     if (rc) return rc;
@@ -738,11 +748,14 @@ int hb_search_batch_elements(hb_index *ix, const void *host_queries, int64_t nq,
                              float *out_dist, int32_t *out_cnt)
 {
     if (!ix || !host_queries || !out_elem || !out_dist) { set_error("hb_search_batch_elements: NULL argument"); return HB_EINVAL; }
+    if (ef < 1 || ef > 1000) { set_error("hnsw.ef_search must be in [1,1000] (got %d)", ef); return HB_EINVAL; }
+    if (nq > 0x7fffffff) { set_error("too many queries in one batch"); return HB_EINVAL; }
     if (nq <= 0) return HB_OK;
     HB_CK(cudaSetDevice(ix->device));
     ScanWs *wsp = ws_for_slot(ix, 0);
     if (!wsp) { set_error("cannot create the scan workspace"); return HB_ECUDA; }
     ScanWs &ws = *wsp;
+    if (ws.pending) { set_error("hb_search_batch_elements: slot 0 still has a batch in flight"); return HB_ESTATE; }
     cudaStream_t s = ws.own_stream;
     const size_t qbytes = (size_t) nq * ix->dim * ix->esize;
     const size_t obytes = (size_t) nq * ef * 8 + (size_t) nq * 4;
@@ -800,6 +813,8 @@ int hb_search_batch_async(hb_index *ix, int slot, const void *host_queries, int6
                           float *out_dist, int32_t *out_cnt)
 {
     if (!ix || !host_queries || !out_tids || !out_dist || k < 1) { set_error("hb_search_batch: bad argument"); return HB_EINVAL; }
+    if (ef < 1 || ef > 1000) { set_error("hnsw.ef_search must be in [1,1000] (got %d)", ef); return HB_EINVAL; }
+    if (nq > 0x7fffffff) { set_error("too many queries in one batch"); return HB_EINVAL; }
     HB_CK(cudaSetDevice(ix->device));
     ScanWs *wsp = ws_for_slot(ix, slot);
     if (!wsp) { set_error("hb_search_batch_async: bad slot %d (0..%d)", slot, ASYNC_SLOTS - 1); return HB_EINVAL; }
@@ -848,6 +863,7 @@ int hb_search_batch(hb_index *ix, const void *host_queries, int64_t nq, int ef, 
                     float *out_dist, int32_t *out_cnt)
 {
     if (!ix || !host_queries || !out_tids || !out_dist || k < 1) { set_error("hb_search_batch: bad argument"); return HB_EINVAL; }
+    if (ef < 1 || ef > 1000) { set_error("hnsw.ef_search must be in [1,1000] (got %d)", ef); return HB_EINVAL; }
     const size_t qbytes = nq > 0 ? (size_t) nq * ix->dim * ix->esize : 0;
     const size_t obytes = nq > 0 ? (size_t) nq * k * 12 + (size_t) nq * 4 : 0;
     if (nq > 0 && qbytes + obytes <= (256 << 10)) {

@@ -21,6 +21,9 @@
 namespace hb {
 
 constexpr int BUILD_WARPS = 4;
+#ifndef HB_MEMO_COLD_GENERIC
+#define HB_MEMO_COLD_GENERIC 0     // link_memo_kernel: rarely taken distance evaluations use the run-time chunk loop (code size)
+#endif
 constexpr int DUP_SLOTS = 8;
 
 struct BuildSearchParams {
@@ -580,7 +583,8 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32, 5) link_memo_kernel(const Li
                             D[a * ld + b] = v; D[b * ld + a] = v;
                         }
                     } else {
-                        memo_fill_matrix<T, IP, NV, G>(g, q0, D, ld, l_id, lm, lane);
+                        // cold (the fill pre-pass filled almost every triangle): the generic row loop keeps the kernel small
+                        memo_fill_matrix<T, IP, (HB_MEMO_COLD_GENERIC ? 0 : NV), (HB_MEMO_COLD_GENERIC ? 2 : G)>(g, q0, D, ld, l_id, lm, lane);
                     }
                     have_matrix = true;
                 }
@@ -626,7 +630,7 @@ __global__ void __launch_bounds__(BUILD_WARPS * 32, 5) link_memo_kernel(const Li
                         __syncwarp();
                         staged = true;
                     }
-                    if (missA | missB) memo_eval_missing<T, IP, NV, G>(g, q0, q1, two, nb, missA, missB, lane, vA, vB);
+                    if (missA | missB) memo_eval_missing<T, IP, (HB_MEMO_COLD_GENERIC ? 0 : NV), (HB_MEMO_COLD_GENERIC ? 2 : G)>(g, q0, q1, two, nb, missA, missB, lane, vA, vB);
                     if (j < lm) { D[lm * ld + j] = vA; D[j * ld + lm] = vA; if (two) D2[j] = vB; }
                 }
                 float dAB = 0.f;

@@ -47,7 +47,9 @@ static int iter_setup(hb_iter *it, const void *host_queries)
     const int64_t nq = it->nq;
     const size_t qbytes = (size_t) nq * ix->dim * ix->esize;
     it->gwords = (int) ((ix->n + 31) / 32 + 1);
-    it->dcap = (int) std::min<long long>(it->max_tuples, ix->n) + 16384;
+    // room for everything max_scan_tuples can visit plus what ONE more search may evaluate before the limit is noticed
+    // (on iid data a resumed ef_search = 1000 search evaluates tens of thousands of rows)
+    it->dcap = (int) std::min<long long>(it->max_tuples, ix->n) + std::max(16384, 64 * it->ef);
     if ((long long) it->dcap > ix->n + 64) it->dcap = (int) ix->n + 64;      // every element is discarded at most once
     it->gcap = it->ef + HB_TIE_LIMIT;
     it->grid = (int) std::min<int64_t>((nq + SCAN_WARPS - 1) / SCAN_WARPS, (int64_t) ix->num_sms * 4);
@@ -110,7 +112,10 @@ int64_t hb_iter_next(hb_iter *it, int32_t *elem, float *dist, int32_t *cnt)
     IterParams p;
     memset(&p, 0, sizeof p);
     p.g = ix->view();
-    p.queries = it->q.p; p.nq = it->nq; p.ef = it->ef; p.mode = it->started ? 1 : 0; p.upper_slots = 1024;
+    p.queries = it->q.p; p.nq = it->nq; p.ef = it->ef; p.mode = it->started ? 1 : 0;
+    // visited table of the ef = 1 descent through the upper layers: a hop adds up to m keys, so large m needs more than 1024 slots
+    p.upper_slots = 1024;
+    while (p.upper_slots < 64 * ix->m && p.upper_slots < 8192) p.upper_slots <<= 1;
     p.max_tuples = it->max_tuples;
     p.bits = it->bits.as<uint32_t>(); p.gwords = it->gwords;
     p.disc_d = it->disc_d.as<float>(); p.disc_id = it->disc_id.as<uint32_t>(); p.dcap = it->dcap;
@@ -131,6 +136,7 @@ int64_t hb_iter_next(hb_iter *it, int32_t *elem, float *dist, int32_t *cnt)
     HB_CK(cudaStreamSynchronize(s));
     if (err == 1) { set_error("a query has more than %d candidates tying exactly at the ef boundary", HB_TIE_LIMIT); return HB_ELIMIT; }
     if (err == 2) { set_error("hb_iter_next: discarded-candidate list full"); return HB_ELIMIT; }
+    if (err == 3) { set_error("hb_iter_next: visited table of the upper-layer descent full (m = %d)", ix->m); return HB_ELIMIT; }
     int64_t total = 0;
     for (int64_t i = 0; i < it->nq; i++) total += cnt[i];
     return total;

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) iter_scan_kernel(const IterPa
             p.out_cnt[qi] = cnt;
             p.disc_n[qi] = min(ds.n, ds.cap);
             p.tuples[qi] = tuples;
-            if (st != ST_OK) atomicExch(p.err, 1);
+            if (st != ST_OK) atomicExch(p.err, st == ST_TABLE ? 3 : 1);
             else if (ds.overflow) atomicExch(p.err, 2);
             atomicAdd(p.totals + 0, (unsigned long long) ctr.n_dist);
             atomicAdd(p.totals + 1, (unsigned long long) ctr.n_hop0);

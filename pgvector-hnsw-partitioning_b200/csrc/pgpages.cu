@@ -107,9 +107,23 @@ extern "C" int hb_index_load_pgvector_pages(hb_index *ix, const void *pages_v, i
             const uint8_t *tup = pg + off;
             const Tid self = { (uint32_t) b, (uint16_t) (i + 1) };
             if (tup[0] == 1) {
+                // HnswElementTupleData: 72 bytes of header, then the vector datum (8 + dim * esize): a tuple that is
+                // shorter cannot be this handle's type (e.g. a halfvec index loaded into a vector_* handle)
+                if ((size_t) len < 80 + (size_t) ix->dim * ix->esize) {
+                    set_error("block %lld item %d: element tuple of %d bytes is too short for %d dimensions of %d bytes (wrong operator class?)",
+                              (long long) b, i + 1, len, ix->dim, ix->esize);
+                    return HB_EINVAL;
+                }
                 id_of[tid_key(self)] = (int32_t) elems.size();
                 elems.push_back({ tup, (uint32_t) b, (uint16_t) (i + 1) });
-            } else if (tup[0] == 2) nbr_tuple[tid_key(self)] = tup;
+            } else if (tup[0] == 2) {
+                if (len < 4 + 6 * (int) rd<uint16_t>(tup + 2)) {
+                    set_error("block %lld item %d: neighbour tuple of %d bytes cannot hold its %d slots", (long long) b, i + 1, len,
+                              (int) rd<uint16_t>(tup + 2));
+                    return HB_EINVAL;
+                }
+                nbr_tuple[tid_key(self)] = tup;
+            }
         }
     }
     const int64_t n = (int64_t) elems.size();
