@@ -535,6 +535,9 @@ def main():
                          # dram__bytes_read.sum + dram__bytes_write.sum of one scan_kernel launch of this exact workload,
                          # from the round's ncu --set full capture (profiles/traffic.json names the report and commit)
                          "traffic": tr["dram_bytes"] if tr else None, "traffic_source": tr.get("source") if tr else None,
+                         # the same launch's measured DRAM bytes over this run's step time: what HBM actually moved
+                         "dram_gbs": round(tr["dram_bytes"] / (ms_per_step / 1e3) / 1e9, 1) if tr else None,
+                         "dram_frac": round(tr["dram_bytes"] / (ms_per_step / 1e3) / 1e9 / hbm_peak, 4) if tr else None,
                          "peak_kind": peak_kind,
                          "frac_of_nominal_8000": round(achieved / 8000.0, 4),
                          "algorithmic_bytes_per_launch": int(alg_per_launch), "kernel": "scan_kernel (batched HnswSearchLayer)",
