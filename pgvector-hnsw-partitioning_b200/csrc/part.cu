@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -284,7 +285,11 @@ hb_part *hb_part_create(int device, int dim, int m, int ef_construction, int met
         pt->owned.push_back(p);
         pt->parts.push_back(ix);
     }
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&pt->xs, cudaStreamNonBlocking) != cudaSuccess) {
+    // the exchange stream gets the highest priority: the scans are persistent kernels that keep every SM full, and the
+    // all-gather's and the merges' CTAs must not queue behind a whole batch of them
+    int prio_lo = 0, prio_hi = 0;
+    if (cudaSetDevice(device) == cudaSuccess) cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithPriority(&pt->xs, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
         set_error("hb_part_create: no CUDA device %d; there is no CPU fallback", device);
         hb_part_free(pt);
         return nullptr;
@@ -371,13 +376,18 @@ int64_t hb_part_build(hb_part *pt, const void *host_vecs, int64_t n, const int64
     auto work = [&](int s) {
         const std::vector<int64_t> &r = rows[s];
         if (r.empty()) return;
-        std::vector<char> buf(r.size() * row);
-        std::vector<int64_t> tids(r.size());
-        for (size_t j = 0; j < r.size(); j++) {
-            memcpy(&buf[j * row], (const char *) host_vecs + (size_t) r[j] * row, row);
-            tids[j] = heap_tids ? heap_tids[r[j]] : r[j];
+        if ((int64_t) r.size() == n) {
+            // every tuple handed in belongs to this partition (a caller that routed already): index it in place
+            done[s] = hb_insert(pt->parts[s], host_vecs, n, heap_tids);
+        } else {
+            std::unique_ptr<char[]> buf(new char[r.size() * row]);       // not value-initialised: written once below
+            std::vector<int64_t> tids(r.size());
+            for (size_t j = 0; j < r.size(); j++) {
+                memcpy(buf.get() + j * row, (const char *) host_vecs + (size_t) r[j] * row, row);
+                tids[j] = heap_tids ? heap_tids[r[j]] : r[j];
+            }
+            done[s] = hb_insert(pt->parts[s], buf.get(), (int64_t) r.size(), tids.data());
         }
-        done[s] = hb_insert(pt->parts[s], buf.data(), (int64_t) r.size(), tids.data());
         if (done[s] < 0) msg[s] = hb_last_error();       // the message lives in this thread: hand it over
     };
     if (no == 1) work(0);
