@@ -673,7 +673,7 @@ def run_partitioned(args, ctx, n, dim):
     pix.counters(reset=True)
     total_steps = warmup + steps
     q_all = gen_set(nq * total_steps, dim, 20260103 + 1000, dev).view(total_steps, nq, dim)   # same on every rank = already broadcast
-    NSLOT = 4                    # HB_PART_SLOTS batches in flight
+    NSLOT = int(os.environ.get("HB_BENCH_PART_SLOTS", "4"))       # batches in flight (at most HB_PART_SLOTS = 4)
     outs = [(torch.empty((nq, k), dtype=torch.int64, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev)) for _ in range(NSLOT)]
     torch.cuda.synchronize()
 

@@ -246,10 +246,12 @@ int hb_elements_to_tids_dev(hb_index *ix, const int32_t *dev_elem, const float *
 /* ---- the partitioned index (the fork's feature): P hash partitions over `world` GPUs -------------- */
 /* One process per GPU.  A row belongs to partition splitmix64(heap_tid) mod P; rank r owns the partitions
  * {p : p mod world == r}, each an ordinary hb_index on the rank's GPU.  A search sends the same query batch
- * to every partition, merges the owned partitions' top-k on the device, exchanges the per-rank lists with ONE
- * ncclAllGather (12 bytes per result) and merges again: every rank ends with the same nq x k answer, ordered
- * by (distance, heap TID).  The handle owns the NCCL communicator (NCCL is dlopen'ed when world > 1); all ranks
- * must make the same sequence of hb_part_search_* calls, as in any NCCL program.  No CPU fallback. */
+ * to every partition, merges the owned partitions' top-k on the device, exchanges the per-rank lists (12 bytes
+ * per result) and merges again: every rank ends with the same nq x k answer, ordered by (distance, heap TID).
+ * The exchange is an all-gather done with stores into the peers' memory over NVLink (buffers mapped through CUDA
+ * IPC, epoch flags instead of a collective kernel) or, with hb_part_set_option("exchange", 0) or when peer mapping
+ * is not possible, ONE ncclAllGather.  The handle owns the NCCL communicator (NCCL is dlopen'ed when world > 1);
+ * all ranks must make the same sequence of hb_part_search_* calls, as in any NCCL program.  No CPU fallback. */
 typedef struct hb_part hb_part;
 #define HB_PART_ID_BYTES 128   /* sizeof(ncclUniqueId) */
 #define HB_PART_SLOTS 4        /* search batches that can be in flight */
@@ -266,7 +268,7 @@ int hb_part_owned(const hb_part *pt, int32_t *partitions);
 /* the hb_index of an owned partition (owned by the hb_part; NULL when another rank owns it) */
 hb_index *hb_part_index(hb_part *pt, int partition);
 int64_t hb_part_size(const hb_part *pt);            /* elements over the owned partitions */
-int hb_part_set_option(hb_part *pt, const char *name, int value);   /* hb_set_option on every owned partition */
+int hb_part_set_option(hb_part *pt, const char *name, int value);   /* "exchange" (see above), else hb_set_option on every owned partition */
 int hb_part_get_counters(hb_part *pt, hb_counters *out, int reset); /* summed over the owned partitions */
 /* ambuild / aminsert: every rank passes the same tuples (or any superset of those it owns); each tuple is
  * indexed by the owner of its partition, owned partitions are built concurrently, no collective.  Returns the

@@ -135,6 +135,125 @@ __global__ void part_status_kernel(const int32_t *__restrict__ err, int32_t *__r
     if (*err) atomicOr(status, 1);
 }
 
+
+// ---- the exchange over peer memory ------------------------------------------------------------
+// With peer access between the ranks' GPUs (NVLink / NVSwitch; buffers opened through CUDA IPC at first use) the
+// all-gather needs no collective kernel: the merge of a rank's owned partitions writes its packed block STRAIGHT INTO
+// every rank's receive buffer (remote stores over NVLink), the last CTA publishes a per-source epoch flag with a
+// system-scope release, and each rank's final merge waits for the world's flags with acquire loads.  A second set of
+// flags acknowledges consumption, so a slot's receive buffer is not overwritten before its owner merged it.  No SM is
+// held by a spinning collective while the persistent scan kernels fill the machine; the NCCL path stays as fallback
+// (option "exchange" = 0, or when peer access cannot be established).
+constexpr int PART_MAX_WORLD = 64;
+struct PeerView {
+    char *base[PART_MAX_WORLD];      // rank r's exchange buffer as mapped in this process (own buffer for r == rank)
+    size_t blk_cap;                  // bytes reserved per source block
+    size_t flags_off;                // int32 ready[world] | int32 ack[world] behind the blocks
+    int rank, world;
+};
+__device__ __forceinline__ int ld_acquire_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// merge the owned partitions' lists (n_lists blocks at `lists`, stride `stride`; n_lists == 0: nothing owned) and
+// store the result into block `rank` of every rank's buffer; then publish ready[rank] = epoch everywhere
+__global__ void part_push_kernel(const char *__restrict__ lists, int n_lists, size_t stride, int64_t nq, int k, PeerView pv,
+                                 int epoch, unsigned int *done_counter)
+{
+    int *my_flags = reinterpret_cast<int *>(pv.base[pv.rank] + pv.flags_off);
+    if (threadIdx.x == 0)
+        for (int r = 0; r < pv.world; r++)
+            while (ld_acquire_sys(my_flags + pv.world + r) < epoch - 1) { }        // rank r consumed this slot's previous batch
+    __syncthreads();
+    const int64_t qi = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi < nq) {
+        uint8_t head[PART_MAX_WORLD];
+        for (int l = 0; l < n_lists; l++) head[l] = 0;
+        const size_t dist_off = (size_t) nq * k * sizeof(int64_t);
+        for (int o = 0; o < k; o++) {
+            int best = -1;
+            float bd = __int_as_float(0x7f800000);
+            int64_t bt = -1;
+            for (int l = 0; l < n_lists; l++) {
+                if (head[l] >= k) continue;
+                const char *b = lists + (size_t) l * stride;
+                const int64_t t = reinterpret_cast<const int64_t *>(b)[qi * k + head[l]];
+                if (t < 0) { head[l] = (uint8_t) k; continue; }
+                const float d = reinterpret_cast<const float *>(b + dist_off)[qi * k + head[l]];
+                if (best < 0 || d < bd || (d == bd && t < bt)) { best = l; bd = d; bt = t; }
+            }
+            if (best >= 0) head[best]++;
+            else { bt = -1; bd = __int_as_float(0x7f800000); }
+            for (int r = 0; r < pv.world; r++) {
+                char *dst = pv.base[r] + (size_t) pv.rank * pv.blk_cap;
+                reinterpret_cast<int64_t *>(dst)[qi * k + o] = bt;
+                reinterpret_cast<float *>(dst + dist_off)[qi * k + o] = bd;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(done_counter, 1u);
+        if (prev == gridDim.x - 1) {
+            *done_counter = 0;
+            __threadfence_system();
+            for (int r = 0; r < pv.world; r++) st_release_sys(reinterpret_cast<int *>(pv.base[r] + pv.flags_off) + pv.rank, epoch);
+        }
+    }
+}
+
+// wait for every rank's block of this epoch, merge them, acknowledge
+__global__ void part_pull_merge_kernel(PeerView pv, int64_t nq, int k, int epoch, char *__restrict__ out, unsigned int *done_counter)
+{
+    int *my_flags = reinterpret_cast<int *>(pv.base[pv.rank] + pv.flags_off);
+    if (threadIdx.x == 0)
+        for (int r = 0; r < pv.world; r++)
+            while (ld_acquire_sys(my_flags + r) < epoch) { }
+    __syncthreads();
+    const int64_t qi = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi < nq) {
+        const char *base = pv.base[pv.rank];
+        uint8_t head[PART_MAX_WORLD];
+        for (int l = 0; l < pv.world; l++) head[l] = 0;
+        const size_t dist_off = (size_t) nq * k * sizeof(int64_t);
+        int64_t *out_t = reinterpret_cast<int64_t *>(out) + qi * k;
+        float *out_d = reinterpret_cast<float *>(out + dist_off) + qi * k;
+        for (int o = 0; o < k; o++) {
+            int best = -1;
+            float bd = 0.f;
+            int64_t bt = 0;
+            for (int l = 0; l < pv.world; l++) {
+                if (head[l] >= k) continue;
+                const char *b = base + (size_t) l * pv.blk_cap;
+                // written by a peer over NVLink: read through L2, never from a stale L1 line of an earlier batch
+                const int64_t t = __ldcg(reinterpret_cast<const long long *>(b) + qi * k + head[l]);
+                if (t < 0) { head[l] = (uint8_t) k; continue; }
+                const float d = __ldcg(reinterpret_cast<const float *>(b + dist_off) + qi * k + head[l]);
+                if (best < 0 || d < bd || (d == bd && t < bt)) { best = l; bd = d; bt = t; }
+            }
+            if (best < 0) { out_t[o] = -1; out_d[o] = __int_as_float(0x7f800000); }
+            else { out_t[o] = bt; out_d[o] = bd; head[best]++; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(done_counter, 1u);
+        if (prev == gridDim.x - 1) {
+            *done_counter = 0;
+            __threadfence_system();
+            for (int r = 0; r < pv.world; r++) st_release_sys(reinterpret_cast<int *>(pv.base[r] + pv.flags_off) + pv.world + pv.rank, epoch);
+        }
+    }
+}
+
 constexpr int PART_SLOTS = 4;
 constexpr int PART_SUBSTREAMS = 4;
 
@@ -144,6 +263,11 @@ struct PartSlot {
     cudaEvent_t ev_q = nullptr, ev_done = nullptr, ev_sub[PART_SUBSTREAMS] = { nullptr, nullptr, nullptr, nullptr };
     DevBuf q, elem, edist, cnt, lists, send, recv, out, status;
     int32_t *h_status = nullptr;                 // pinned
+    // peer-memory exchange: this rank's buffer [world blocks | ready flags | ack flags], the peers' mapped in
+    char *xbuf = nullptr;
+    char *peer[PART_MAX_WORLD] = { nullptr };
+    size_t xblk_cap = 0, xflags_off = 0;
+    int epoch = 0;
     bool pending = false, tail_queued = false;
     int64_t nq = 0;
     int k = 0, ef = 0, nsub = 0, out_dev = 0;
@@ -162,6 +286,9 @@ struct hb_part {
     std::vector<hb_index *> parts;               // handles of the owned partitions, same order
     ncclComm_t comm = nullptr;
     cudaStream_t xs = nullptr;                   // the exchange stream: every collective, in call order
+    int exchange = 1;                            // 1 = stores into peer memory + flags, 0 = ncclAllGather
+    bool peer_failed = false;                    // peer access could not be set up: NCCL from then on
+    DevBuf xmisc;                                // counters of the push / pull kernels, handle exchange scratch
     PartSlot slots[PART_SLOTS];
     uint64_t issued = 0;                         // batches issued so far (diagnostics)
 };
@@ -199,6 +326,88 @@ static void slot_release(PartSlot &S)
     S = PartSlot();
 }
 
+
+// (Re)allocate slot S's exchange buffer for blocks of `blk` bytes and map every peer's into this process.  Collective:
+// every rank calls it at the same point (the first batch of a slot, or a larger nq / k), because the IPC handles are
+// exchanged with one ncclAllGather.  Returns HB_OK and sets pt->peer_failed when peer access is not available.
+static void peer_close(hb_part *pt, PartSlot &S)
+{
+    for (int r = 0; r < pt->world; r++) {
+        if (S.peer[r] && r != pt->rank) cudaIpcCloseMemHandle(S.peer[r]);
+        S.peer[r] = nullptr;
+    }
+}
+static void peer_unmap(hb_part *pt, PartSlot &S)
+{
+    peer_close(pt, S);
+    if (S.xbuf) cudaFree(S.xbuf);
+    S.xbuf = nullptr; S.xblk_cap = 0;
+}
+// every rank has closed its mappings of the others' buffers before anybody frees one
+static void peer_barrier(hb_part *pt)
+{
+    NcclApi *nc = nccl_api();
+    if (!nc || !pt->comm || !pt->xmisc.p) return;
+    char *scratch = pt->xmisc.as<char>() + 256;
+    if (nc->AllGather(scratch, scratch + 64, 4, ncclChar, pt->comm, pt->xs) == ncclSuccess) cudaStreamSynchronize(pt->xs);
+}
+
+static int peer_ensure(hb_part *pt, PartSlot &S, size_t blk)
+{
+    if (pt->peer_failed || blk <= S.xblk_cap) return HB_OK;
+    NcclApi *nc = nccl_api();
+    if (!nc) return HB_ECUDA;
+    HB_CK(cudaDeviceSynchronize());                        // nothing of this handle is in flight on a buffer about to go
+    if (S.xbuf) { peer_close(pt, S); peer_barrier(pt); }
+    peer_unmap(pt, S);
+    const int W = pt->world;
+    const size_t cap = (blk + blk / 4 + 255) & ~(size_t) 255;
+    const size_t flags_off = cap * W;
+    const size_t total = flags_off + sizeof(int) * 2 * W + 64;
+    HB_CK(cudaMalloc(&S.xbuf, total));
+    HB_CK(cudaMemset(S.xbuf, 0, total));
+    HB_CK(cudaDeviceSynchronize());                        // flags are zero before any peer can learn the address
+    S.epoch = 0;
+    cudaIpcMemHandle_t mine;
+    bool ok = cudaIpcGetMemHandle(&mine, S.xbuf) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); memset(&mine, 0, sizeof mine); }
+    // all-gather {ok, handle}
+    struct Rec { int ok; int pad; cudaIpcMemHandle_t h; };
+    HB_CK(pt->xmisc.ensure(256 + sizeof(Rec) * (size_t) (W + 1)));
+    Rec *d_send = reinterpret_cast<Rec *>(pt->xmisc.as<char>() + 256), *d_recv = d_send + 1;
+    Rec rec;
+    rec.ok = ok ? 1 : 0; rec.pad = 0; rec.h = mine;
+    std::vector<Rec> all(W);
+    HB_CK(cudaMemcpyAsync(d_send, &rec, sizeof rec, cudaMemcpyHostToDevice, pt->xs));
+    HB_NCCL(nc->AllGather(d_send, d_recv, sizeof(Rec), ncclChar, pt->comm, pt->xs));
+    HB_CK(cudaMemcpyAsync(all.data(), d_recv, sizeof(Rec) * W, cudaMemcpyDeviceToHost, pt->xs));
+    HB_CK(cudaStreamSynchronize(pt->xs));
+    for (int r = 0; r < W; r++) ok = ok && all[r].ok;
+    if (ok) {
+        for (int r = 0; r < W && ok; r++) {
+            if (r == pt->rank) { S.peer[r] = S.xbuf; continue; }
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; }
+            S.peer[r] = (char *) ptr;
+        }
+    }
+    // agree on the outcome: one rank that cannot map a peer sends everybody to the NCCL path
+    rec.ok = ok ? 1 : 0;
+    HB_CK(cudaMemcpyAsync(d_send, &rec, sizeof rec, cudaMemcpyHostToDevice, pt->xs));
+    HB_NCCL(nc->AllGather(d_send, d_recv, sizeof(Rec), ncclChar, pt->comm, pt->xs));
+    HB_CK(cudaMemcpyAsync(all.data(), d_recv, sizeof(Rec) * W, cudaMemcpyDeviceToHost, pt->xs));
+    HB_CK(cudaStreamSynchronize(pt->xs));
+    for (int r = 0; r < W; r++) ok = ok && all[r].ok;
+    if (!ok) {
+        peer_unmap(pt, S);
+        pt->peer_failed = true;
+        return HB_OK;
+    }
+    S.xblk_cap = cap;
+    S.xflags_off = flags_off;
+    return HB_OK;
+}
+
 // the exchange + final merge of one batch, queued on the exchange stream
 static int queue_tail(hb_part *pt, PartSlot &S)
 {
@@ -210,25 +419,41 @@ static int queue_tail(hb_part *pt, PartSlot &S)
     cudaStream_t xs = pt->xs;
     for (int j = 0; j < S.nsub; j++) HB_CK(cudaStreamWaitEvent(xs, S.ev_sub[j], 0));
     const int no = (int) pt->owned.size();
-    char *local = nullptr;
-    if (no == 0) {
-        part_pad_kernel<<<(int) ((nq * k + 255) / 256), 256, 0, xs>>>(S.send.as<char>(), nq, k);
-        local = S.send.as<char>();
-    } else if (no == 1) {
-        local = S.lists.as<char>();                      // one partition: its list is the rank's list
-    } else {
-        part_merge_kernel<<<tgrid, 128, 0, xs>>>(S.lists.as<char>(), no, blk, nq, k, S.send.as<char>());
-        local = S.send.as<char>();
-    }
-    HB_CK(cudaGetLastError());
-    char *result = local;
-    if (pt->world > 1) {
-        NcclApi *nc = nccl_api();
-        if (!nc) return HB_ECUDA;
-        HB_NCCL(nc->AllGather(local, S.recv.p, blk, ncclChar, pt->comm, xs));
-        part_merge_kernel<<<tgrid, 128, 0, xs>>>(S.recv.as<char>(), pt->world, blk, nq, k, S.out.as<char>());
+    char *result = nullptr;
+    if (pt->world > 1 && pt->exchange == 1 && !pt->peer_failed && S.xbuf && blk <= S.xblk_cap) {
+        // merge of the owned partitions pushed straight into every rank's receive block; flags instead of a collective
+        PeerView pv;
+        memset(&pv, 0, sizeof pv);
+        for (int r = 0; r < pt->world; r++) pv.base[r] = S.peer[r];
+        pv.blk_cap = S.xblk_cap; pv.flags_off = S.xflags_off; pv.rank = pt->rank; pv.world = pt->world;
+        S.epoch++;
+        unsigned int *counters = pt->xmisc.as<unsigned int>();
+        part_push_kernel<<<tgrid, 128, 0, xs>>>(S.lists.as<char>(), no, blk, nq, k, pv, S.epoch, counters + 2 * (int) (&S - pt->slots));
+        HB_CK(cudaGetLastError());
+        part_pull_merge_kernel<<<tgrid, 128, 0, xs>>>(pv, nq, k, S.epoch, S.out.as<char>(), counters + 2 * (int) (&S - pt->slots) + 1);
         HB_CK(cudaGetLastError());
         result = S.out.as<char>();
+    } else {
+        char *local = nullptr;
+        if (no == 0) {
+            part_pad_kernel<<<(int) ((nq * k + 255) / 256), 256, 0, xs>>>(S.send.as<char>(), nq, k);
+            local = S.send.as<char>();
+        } else if (no == 1) {
+            local = S.lists.as<char>();                      // one partition: its list is the rank's list
+        } else {
+            part_merge_kernel<<<tgrid, 128, 0, xs>>>(S.lists.as<char>(), no, blk, nq, k, S.send.as<char>());
+            local = S.send.as<char>();
+        }
+        HB_CK(cudaGetLastError());
+        result = local;
+        if (pt->world > 1) {
+            NcclApi *nc = nccl_api();
+            if (!nc) return HB_ECUDA;
+            HB_NCCL(nc->AllGather(local, S.recv.p, blk, ncclChar, pt->comm, xs));
+            part_merge_kernel<<<tgrid, 128, 0, xs>>>(S.recv.as<char>(), pt->world, blk, nq, k, S.out.as<char>());
+            HB_CK(cudaGetLastError());
+            result = S.out.as<char>();
+        }
     }
     HB_CK(cudaEventRecord(S.ev_done, xs));
     HB_CK(cudaStreamWaitEvent(S.s, S.ev_done, 0));
@@ -260,7 +485,11 @@ void hb_part_free(hb_part *pt)
     if (!pt) return;
     cudaSetDevice(pt->device);
     cudaDeviceSynchronize();
-    for (auto &S : pt->slots) slot_release(S);
+    bool any_peer = false;
+    for (auto &S : pt->slots) { if (S.xbuf) any_peer = true; peer_close(pt, S); }
+    if (any_peer) peer_barrier(pt);
+    for (auto &S : pt->slots) { peer_unmap(pt, S); slot_release(S); }
+    pt->xmisc.release();
     if (pt->comm) { NcclApi *nc = nccl_api(); if (nc) nc->CommDestroy(pt->comm); }
     if (pt->xs) cudaStreamDestroy(pt->xs);
     for (hb_index *ix : pt->parts) hb_index_free(ix);
@@ -289,11 +518,19 @@ hb_part *hb_part_create(int device, int dim, int m, int ef_construction, int met
     // all-gather's and the merges' CTAs must not queue behind a whole batch of them
     int prio_lo = 0, prio_hi = 0;
     if (cudaSetDevice(device) == cudaSuccess) cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (const char *e = getenv("HB_PART_XS_PRIORITY")) { if (atoi(e) == 0) prio_hi = prio_lo; }      // experiments: 0 = default priority
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithPriority(&pt->xs, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
         set_error("hb_part_create: no CUDA device %d; there is no CPU fallback", device);
         hb_part_free(pt);
         return nullptr;
     }
+    if (pt->xmisc.ensure(8192) != cudaSuccess || cudaMemset(pt->xmisc.p, 0, 8192) != cudaSuccess) {
+        set_error("hb_part_create: out of device memory");
+        hb_part_free(pt);
+        return nullptr;
+    }
+    if (const char *e = getenv("HB_PART_EXCHANGE")) pt->exchange = atoi(e);                          // experiments: 0 = ncclAllGather
+    if (world > PART_MAX_WORLD) pt->exchange = 0;
     if (world > 1) {
         NcclApi *nc = nccl_api();
         if (!nc) { hb_part_free(pt); return nullptr; }
@@ -335,6 +572,7 @@ int64_t hb_part_size(const hb_part *pt)
 int hb_part_set_option(hb_part *pt, const char *name, int value)
 {
     if (!pt) return HB_EINVAL;
+    if (name && !strcmp(name, "exchange")) { pt->exchange = value; return HB_OK; }      // 1 = peer-memory stores + flags, 0 = ncclAllGather
     for (hb_index *ix : pt->parts) { const int rc = hb_set_option(ix, name, value); if (rc) return rc; }
     return HB_OK;
 }
@@ -430,7 +668,11 @@ int hb_part_search_async(hb_part *pt, int slot, const void *queries, int queries
     HB_CK(S.cnt.ensure(sizeof(int32_t) * (size_t) std::max(no, 1) * nq));
     HB_CK(S.lists.ensure(blk * std::max(no, 1)));
     HB_CK(S.send.ensure(blk));
-    if (pt->world > 1) { HB_CK(S.recv.ensure(blk * pt->world)); HB_CK(S.out.ensure(blk)); }
+    if (pt->world > 1) {
+        HB_CK(S.recv.ensure(blk * pt->world));
+        HB_CK(S.out.ensure(blk));
+        if (pt->exchange == 1) { rc = peer_ensure(pt, S, blk); if (rc) return rc; }
+    }
     S.nq = nq; S.k = k; S.ef = ef_search; S.out_tids = out_tids; S.out_dist = out_dist; S.out_dev = out_on_device;
     S.nsub = std::min(std::max(no, 1), PART_SUBSTREAMS);
     S.tail_queued = false;

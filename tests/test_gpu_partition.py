@@ -82,6 +82,24 @@ def _nccl_worker(rank, world, port, outq):
         pix.search_wait(b)
     for b in range(3):
         assert (outs[b][0] == outs_b[b][0]).all() and (outs[b][1] == outs_b[b][1]).all()
+    # the exchange over peer memory (default) and the ncclAllGather fallback give the same answer; two rounds per slot so
+    # that the epoch / acknowledge flags of a reused slot are exercised
+    for exchange in (0, 1):
+        pix.set_option("exchange", exchange)
+        for rnd in range(2):
+            outs_x = [(np.empty((nq, k), np.int64), np.empty((nq, k), np.float32)) for _ in range(3)]
+            for b in range(3):
+                pix.search_async(b, qs[b].ctypes.data, nq, k, ef, outs_x[b][0].ctypes.data, outs_x[b][1].ctypes.data, root=-1)
+            for b in range(3):
+                pix.search_wait(b)
+            for b in range(3):
+                assert (outs[b][0] == outs_x[b][0]).all() and (outs[b][1] == outs_x[b][1]).all(), (exchange, rnd, b)
+    # a larger batch re-allocates (and re-maps) the exchange buffers
+    qbig = np.concatenate(qs)
+    ob = (np.empty((3 * nq, k), np.int64), np.empty((3 * nq, k), np.float32))
+    pix.search_async(1, qbig.ctypes.data, 3 * nq, k, ef, ob[0].ctypes.data, ob[1].ctypes.data, root=-1)
+    pix.search_wait(1)
+    assert (ob[0] == np.concatenate([o[0] for o in outs])).all()
     # the oracle's answer for the partitions this rank owns, on the very graphs the GPU built
     per = {}
     for p, ix in pix.parts.items():
