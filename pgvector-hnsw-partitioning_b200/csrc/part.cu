@@ -162,16 +162,20 @@ __device__ __forceinline__ void st_release_sys(int *p, int v)
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// one warp waits until flags[0 .. world) have all reached `epoch` (a kernel of its own, so that the waiting holds one
+// warp and not the CTAs of the merge that follows it in the stream)
+__global__ void part_wait_kernel(const int *flags, int world, int epoch)
+{
+    for (int r = threadIdx.x; r < world; r += 32)
+        while (ld_acquire_sys(flags + r) < epoch) { }
+}
+
 // merge the owned partitions' lists (n_lists blocks at `lists`, stride `stride`; n_lists == 0: nothing owned) and
 // store the result into block `rank` of every rank's buffer; then publish ready[rank] = epoch everywhere
 __global__ void part_push_kernel(const char *__restrict__ lists, int n_lists, size_t stride, int64_t nq, int k, PeerView pv,
                                  int epoch, unsigned int *done_counter)
 {
-    int *my_flags = reinterpret_cast<int *>(pv.base[pv.rank] + pv.flags_off);
-    if (threadIdx.x == 0)
-        for (int r = 0; r < pv.world; r++)
-            while (ld_acquire_sys(my_flags + pv.world + r) < epoch - 1) { }        // rank r consumed this slot's previous batch
-    __syncthreads();
+    // (part_wait_kernel ran before: every rank has consumed this slot's previous batch)
     const int64_t qi = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (qi < nq) {
         uint8_t head[PART_MAX_WORLD];
@@ -213,11 +217,7 @@ __global__ void part_push_kernel(const char *__restrict__ lists, int n_lists, si
 // wait for every rank's block of this epoch, merge them, acknowledge
 __global__ void part_pull_merge_kernel(PeerView pv, int64_t nq, int k, int epoch, char *__restrict__ out, unsigned int *done_counter)
 {
-    int *my_flags = reinterpret_cast<int *>(pv.base[pv.rank] + pv.flags_off);
-    if (threadIdx.x == 0)
-        for (int r = 0; r < pv.world; r++)
-            while (ld_acquire_sys(my_flags + r) < epoch) { }
-    __syncthreads();
+    // (part_wait_kernel ran before: every rank's block of this epoch has arrived)
     const int64_t qi = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (qi < nq) {
         const char *base = pv.base[pv.rank];
@@ -428,8 +428,11 @@ static int queue_tail(hb_part *pt, PartSlot &S)
         pv.blk_cap = S.xblk_cap; pv.flags_off = S.xflags_off; pv.rank = pt->rank; pv.world = pt->world;
         S.epoch++;
         unsigned int *counters = pt->xmisc.as<unsigned int>();
+        const int *my_flags = reinterpret_cast<const int *>(S.xbuf + S.xflags_off);
+        part_wait_kernel<<<1, 32, 0, xs>>>(my_flags + pt->world, pt->world, S.epoch - 1);          // acknowledgements of the slot's previous batch
         part_push_kernel<<<tgrid, 128, 0, xs>>>(S.lists.as<char>(), no, blk, nq, k, pv, S.epoch, counters + 2 * (int) (&S - pt->slots));
         HB_CK(cudaGetLastError());
+        part_wait_kernel<<<1, 32, 0, xs>>>(my_flags, pt->world, S.epoch);                           // every rank's block of this batch
         part_pull_merge_kernel<<<tgrid, 128, 0, xs>>>(pv, nq, k, S.epoch, S.out.as<char>(), counters + 2 * (int) (&S - pt->slots) + 1);
         HB_CK(cudaGetLastError());
         result = S.out.as<char>();
