@@ -164,10 +164,15 @@ __device__ __forceinline__ void st_release_sys(int *p, int v)
 
 // one warp waits until flags[0 .. world) have all reached `epoch` (a kernel of its own, so that the waiting holds one
 // warp and not the CTAs of the merge that follows it in the stream)
-__global__ void part_wait_kernel(const int *flags, int world, int epoch)
+// A rank that never arrives (it failed, or the ranks' call sequences diverged) must not hang the GPU: after ~20 s the
+// wait gives up and flags the slot's status word (bit 1), which hb_part_search_wait reports.
+__global__ void part_wait_kernel(const int *flags, int world, int epoch, int32_t *status)
 {
+    const long long t0 = clock64();
     for (int r = threadIdx.x; r < world; r += 32)
-        while (ld_acquire_sys(flags + r) < epoch) { }
+        while (ld_acquire_sys(flags + r) < epoch) {
+            if (clock64() - t0 > 40000000000ll) { atomicOr(status, 2); return; }
+        }
 }
 
 // merge the owned partitions' lists (n_lists blocks at `lists`, stride `stride`; n_lists == 0: nothing owned) and
@@ -429,10 +434,10 @@ static int queue_tail(hb_part *pt, PartSlot &S)
         S.epoch++;
         unsigned int *counters = pt->xmisc.as<unsigned int>();
         const int *my_flags = reinterpret_cast<const int *>(S.xbuf + S.xflags_off);
-        part_wait_kernel<<<1, 32, 0, xs>>>(my_flags + pt->world, pt->world, S.epoch - 1);          // acknowledgements of the slot's previous batch
+        part_wait_kernel<<<1, 32, 0, xs>>>(my_flags + pt->world, pt->world, S.epoch - 1, S.status.as<int32_t>());          // acknowledgements of the slot's previous batch
         part_push_kernel<<<tgrid, 128, 0, xs>>>(S.lists.as<char>(), no, blk, nq, k, pv, S.epoch, counters + 2 * (int) (&S - pt->slots));
         HB_CK(cudaGetLastError());
-        part_wait_kernel<<<1, 32, 0, xs>>>(my_flags, pt->world, S.epoch);                           // every rank's block of this batch
+        part_wait_kernel<<<1, 32, 0, xs>>>(my_flags, pt->world, S.epoch, S.status.as<int32_t>());                           // every rank's block of this batch
         part_pull_merge_kernel<<<tgrid, 128, 0, xs>>>(pv, nq, k, S.epoch, S.out.as<char>(), counters + 2 * (int) (&S - pt->slots) + 1);
         HB_CK(cudaGetLastError());
         result = S.out.as<char>();
@@ -763,6 +768,10 @@ int hb_part_search_wait(hb_part *pt, int slot)
     }
     HB_CK(cudaStreamSynchronize(S.s));
     S.pending = false;
+    if (*S.h_status & 2) {
+        set_error("hb_part_search: a rank did not deliver its results within 20 s (failed rank, or the ranks' call sequences differ)");
+        return HB_ECUDA;
+    }
     if (*S.h_status) {
         set_error("a query has more than %d candidates tying exactly at the ef boundary", HB_TIE_LIMIT);
         return HB_ELIMIT;
