@@ -197,6 +197,9 @@ int hb_search_batch_elements(hb_index *ix, const void *host_queries, int64_t nq,
 int hb_search_batch_dev(hb_index *ix, const void *dev_queries, int64_t nq, int ef_search,
                         int32_t *dev_out_elem, float *dev_out_dist, int32_t *dev_out_cnt,
                         void *stream);
+/* waits for `stream` and returns the status of the last hb_search_batch_dev queued on it: HB_ELIMIT when a query
+ * of that batch had more than HB_TIE_LIMIT candidates tying at the ef boundary (its result count is 0) */
+int hb_search_batch_status(hb_index *ix, void *stream);
 /* one HnswSearchLayer call from explicit entry points (unit-test surface of the layer kernel):
  * ep nq x nep element ids; out nq x max(ef,nep) */
 int hb_search_layer(hb_index *ix, const void *host_queries, int64_t nq, const int32_t *ep, int nep,

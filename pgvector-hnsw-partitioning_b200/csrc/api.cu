@@ -744,6 +744,17 @@ int hb_search_batch_dev(hb_index *ix, const void *dev_queries, int64_t nq, int e
     return scan_dev(ix, *ws, dev_queries, nq, ef, dev_out_elem, dev_out_dist, dev_out_cnt, (cudaStream_t) stream, nullptr, 0, 0);
 }
 
+// the error word of the last hb_search_batch_dev on `stream` (the device API cannot fail asynchronously otherwise):
+// waits for the stream, HB_ELIMIT when a query of that batch exceeded HB_TIE_LIMIT boundary ties (its count is 0)
+int hb_search_batch_status(hb_index *ix, void *stream)
+{
+    if (!ix) { set_error("hb_search_batch_status: NULL index"); return HB_EINVAL; }
+    auto it = ix->stream_ws.find(stream);
+    if (it == ix->stream_ws.end() || !it->second->misc.p) return HB_OK;
+    HB_CK(cudaSetDevice(ix->device));
+    return check_status(ix, *it->second, 0, (cudaStream_t) stream);
+}
+
 int hb_search_batch_elements(hb_index *ix, const void *host_queries, int64_t nq, int ef, int32_t *out_elem,
                              float *out_dist, int32_t *out_cnt)
 {

@@ -97,6 +97,7 @@ _SIGS = {
     "hb_search_batch_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "hb_search_batch_elements": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_search_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_search_batch_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hb_search_layer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_get_counters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "hb_get_per_query_counters": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
@@ -370,6 +371,10 @@ class HnswIndex:
         self._ck(self._L.hb_search_batch_dev(self._h, C.c_void_p(dev_queries), nq, ef_search, C.c_void_p(dev_elem),
                                              C.c_void_p(dev_dist), C.c_void_p(dev_cnt), C.c_void_p(stream)),
                  "hb_search_batch_dev")
+
+    def search_status(self, stream=0):
+        """waits for `stream`; raises if the last search_dev on it hit the tie-tail limit"""
+        self._ck(self._L.hb_search_batch_status(self._h, C.c_void_p(stream)), "hb_search_batch_status")
 
     def elements_to_tids_dev(self, dev_elem, dev_dist, nq, ef, k, dev_tids, dev_tdist, stream=0):
         self._ck(self._L.hb_elements_to_tids_dev(self._h, C.c_void_p(dev_elem), C.c_void_p(dev_dist), nq, ef, k,

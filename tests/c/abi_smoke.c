@@ -16,7 +16,7 @@ int main(void)
     REF(hb_index_load); REF(hb_index_load_pgvector_pages); REF(hb_pgvector_pages_info); REF(hb_index_upper_rows); REF(hb_index_export);
     REF(hb_beginscan); REF(hb_rescan); REF(hb_gettuple); REF(hb_endscan); REF(hb_scan_set_iterative);
     REF(hb_iter_begin); REF(hb_iter_next); REF(hb_iter_tuples); REF(hb_iter_end); REF(hb_search_batch_filtered);
-    REF(hb_search_batch); REF(hb_search_batch_async); REF(hb_search_batch_wait); REF(hb_search_batch_elements); REF(hb_search_batch_dev);
+    REF(hb_search_batch); REF(hb_search_batch_async); REF(hb_search_batch_wait); REF(hb_search_batch_elements); REF(hb_search_batch_dev); REF(hb_search_batch_status);
     REF(hb_distance_batch); REF(hb_distance_batch_dev); REF(hb_normalize); REF(hb_bruteforce);
     REF(hb_partition_of); REF(hb_partition_route); REF(hb_merge_topk_dev); REF(hb_elements_to_tids_dev);
     REF(hb_part_unique_id); REF(hb_part_create); REF(hb_part_free); REF(hb_part_owned); REF(hb_part_index); REF(hb_part_size);
