@@ -6,6 +6,7 @@
 #include "index.h"
 #include "scan_kernel.cuh"
 #include "scan_reg.cuh"
+#include "scan_cta.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -156,6 +157,7 @@ __global__ void merge_topk_kernel(const int64_t *__restrict__ tids, const float 
     cudaError_t scan_fast_##name(const ScanParams &, int, int, cudaStream_t, ScanLaunchInfo *);               \
     cudaError_t scan_slow_##name(const ScanParams &, int, int, cudaStream_t, ScanLaunchInfo *);               \
     cudaError_t scan_reg_##name(const ScanParams &, int, int, int, cudaStream_t, ScanLaunchInfo *);           \
+    cudaError_t scan_cta_##name(const ScanParams &, int, cudaStream_t);                                       \
     cudaError_t dist_##name(const DistBatchParams &, cudaStream_t);
 HB_DECL(f32_l2) HB_DECL(f32_ip) HB_DECL(f16_l2) HB_DECL(f16_ip) HB_DECL(f32_l1) HB_DECL(f16_l1)
 #undef HB_DECL
@@ -170,6 +172,11 @@ scan_launch_fn get_scan_launcher(int dtype, int kind, bool slow)
 scan_reg_launch_fn get_scan_reg_launcher(int dtype, int kind)
 {
     static const scan_reg_launch_fn tab[2][3] = { { scan_reg_f32_l2, scan_reg_f32_ip, scan_reg_f32_l1 }, { scan_reg_f16_l2, scan_reg_f16_ip, scan_reg_f16_l1 } };
+    return tab[dtype == HB_F32 ? 0 : 1][kind];
+}
+scan_cta_launch_fn get_scan_cta_launcher(int dtype, int kind)
+{
+    static const scan_cta_launch_fn tab[2][3] = { { scan_cta_f32_l2, scan_cta_f32_ip, scan_cta_f32_l1 }, { scan_cta_f16_l2, scan_cta_f16_ip, scan_cta_f16_l1 } };
     return tab[dtype == HB_F32 ? 0 : 1][kind];
 }
 dist_launch_fn get_dist_launcher(int dtype, int kind)
@@ -709,7 +716,9 @@ static int scan_dev(hb_index *ix, ScanWs &ws, const void *dev_queries, int64_t n
     HB_CK(cudaEventRecord(ws.ev0, s));
     p.work = misc + 0;
     ScanLaunchInfo info;
-    if (regR) HB_CK(get_scan_reg_launcher(ix->dtype, ip)(p, regR, ix->num_sms, ix->opt_grid, s, &info));
+    const size_t qsmem = (size_t) ix->nvec * (ix->dtype == HB_F32 ? 4 : 8) * 4;
+    if (use_cta_scan(p, ix->num_sms, qsmem, dev_ep, ix->opt_variant)) HB_CK(get_scan_cta_launcher(ix->dtype, ip)(p, ix->num_sms, s));
+    else if (regR) HB_CK(get_scan_reg_launcher(ix->dtype, ip)(p, regR, ix->num_sms, ix->opt_grid, s, &info));
     else HB_CK(get_scan_launcher(ix->dtype, ip, false)(p, ix->num_sms, ix->opt_grid, s, &info));
     // queries whose tie tail (or overflow table) outgrew the fast path run again with a bitmap in HBM
     ScanParams ps = p;

@@ -161,6 +161,9 @@ scan_launch_fn get_scan_launcher(int dtype, int kind, bool slow);
 // register-list scan (scan_reg.cuh): R = registers per lane and field holding the W list
 typedef cudaError_t (*scan_reg_launch_fn)(const ScanParams &, int R, int num_sms, int max_grid, cudaStream_t, ScanLaunchInfo *);
 scan_reg_launch_fn get_scan_reg_launcher(int dtype, int kind);
+// CTA-per-query scan for small batches (scan_cta.cuh)
+typedef cudaError_t (*scan_cta_launch_fn)(const ScanParams &, int num_sms, cudaStream_t);
+scan_cta_launch_fn get_scan_cta_launcher(int dtype, int kind);
 
 struct DistBatchParams;
 typedef cudaError_t (*dist_launch_fn)(const DistBatchParams &, cudaStream_t);

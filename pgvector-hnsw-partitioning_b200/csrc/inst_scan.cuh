@@ -4,6 +4,7 @@
 #include "index.h"
 #include "scan_kernel.cuh"
 #include "scan_reg.cuh"
+#include "scan_cta.cuh"
 
 namespace hb {
 cudaError_t HB_CAT(scan_fast_, HBI_NAME)(const ScanParams &p, int sms, int mg, cudaStream_t s, ScanLaunchInfo *i)
@@ -18,6 +19,7 @@ cudaError_t HB_CAT(scan_reg_, HBI_NAME)(const ScanParams &p, int R, int sms, int
 {
     return launch_scan_reg_t<HBI_T, HBI_IP>(p, R, sms, mg, s, i);
 }
+cudaError_t HB_CAT(scan_cta_, HBI_NAME)(const ScanParams &p, int sms, cudaStream_t s) { return launch_scan_cta_t<HBI_T, HBI_IP>(p, sms, s); }
 cudaError_t HB_CAT(dist_, HBI_NAME)(const DistBatchParams &p, cudaStream_t s) { return launch_dist_t<HBI_T, HBI_IP>(p, s); }
 }   // namespace hb
 

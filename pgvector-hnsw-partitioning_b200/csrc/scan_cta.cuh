@@ -1,0 +1,250 @@
+// scan_cta.cuh -- the scan for a HANDFUL of queries (one backend's amrescan + amgettuple, small batches): one CTA of
+// four warps per query instead of one warp.
+//
+// Same algorithm and expansion order as scan_kernel.cuh (role: hnswscan.c GetScanItems + hnswutils.c HnswSearchLayer
+// [RECALL; reference mount empty, /root/reference/README.md:1]), so ids, distances and counters are identical.  A single
+// scan is a chain of dependent expansions; with few queries the GPU is idle and what matters is the length of one link
+// of that chain, not throughput.  Per expansion:
+//   warp 0   picks the nearest unexpanded entry, reads its neighbour list, filters it through the visited table and
+//            compacts the new candidates into shared memory;
+//   warp 1   meanwhile looks one expansion ahead: it reads the neighbour list of the NEXT nearest unexpanded entry and
+//            asks the rows of its not-yet-visited neighbours into L2 (prefetch only: nothing observable changes), so
+//            that when that entry is expanded next -- the usual case -- its list and rows come from L2, not HBM;
+//   warps 0-3 evaluate the new candidates' distances, a quarter each (canonical order, so the same bits);
+//   warp 0   admits and inserts in neighbour order, as the sequential loop does.
+// Queries whose tie tail or visited set outgrow shared memory go to the large-visited-set path like everywhere else.
+#pragma once
+#include "scan_kernel.cuh"
+
+namespace hb {
+
+constexpr int CTA_WARPS = 4;
+constexpr int CTA_SLOTS = 8192;          // visited table of the layer-0 search (32 kB: one CTA per SM is plenty)
+
+template <typename T> __host__ __device__ inline size_t scan_cta_smem(int nvec, int capW)
+{
+    // query | W (d, id) | visited table | cbuf ids | dbuf distances | control words
+    return (((size_t) nvec * Vec<T>::VEC * 4 + (size_t) capW * 8 + (size_t) CTA_SLOTS * 4 + 64 * 8 + 64) + 15) & ~(size_t) 15;
+}
+
+template <typename T, int IP, int NV>
+__device__ __forceinline__ int search_layer_cta(const GraphView &g, WList &w, VisitedHash &vs, const float *q, int32_t *cbuf,
+                                                float *dbuf, volatile int *ctl, int ef, int lc, int lane, int warp,
+                                                QueryCounters &ctr)
+{
+    // ctl[0] = candidate to expand (-1: layer done), ctl[1] = number of new candidates, ctl[2] = status,
+    // ctl[3] = next nearest unexpanded candidate (-1: none)
+    const int deg = lc == 0 ? 2 * g.m : g.m;
+    int low = 0;                       // warp 0 only
+    NoDiscard nd;
+    for (;;) {
+        if (warp == 0) {
+            int idx = -1, nxt = -1;
+            for (int base = low; base < w.L && idx < 0; base += 32) {
+                const int i = base + lane;
+                const unsigned b = __ballot_sync(FULL, i < w.L && !(w.id[i] & EXP_BIT));
+                if (b) {
+                    idx = base + __ffs(b) - 1;
+                    const unsigned b2 = b & (b - 1);
+                    if (b2) nxt = (int) (w.id[base + __ffs(b2) - 1] & ID_MASK);
+                }
+            }
+            int cid = -1;
+            if (idx >= 0) {
+                cid = (int) (w.id[idx] & ID_MASK);
+                __syncwarp();
+                if (lane == 0) w.id[idx] |= EXP_BIT;
+                low = idx + 1;
+                if (lc == 0) ctr.n_hop0++; else ctr.n_hopu++;
+            }
+            if (lane == 0) { ctl[0] = cid; ctl[3] = nxt; ctl[1] = 0; }
+        }
+        __syncthreads();
+        const int cid = ctl[0];
+        if (cid < 0) break;
+        const int32_t *list = lc == 0 ? g.nbr0 + (size_t) cid * deg : g.nbru + ((size_t) g.uoff[cid] + (lc - 1)) * g.m;
+        // the neighbour list goes through in chunks of 32, each filtered, evaluated and inserted before the next one --
+        // the order in which the sequential loop meets the neighbours
+        for (int cb = 0; cb < deg; cb += 32) {
+            if (warp == 0) {
+                int st = ST_OK, nnew = 0;
+                if (cb == 0 && !vs.room(deg)) st = ST_TABLE;
+                if (st == ST_OK) {
+                    const int i = cb + lane;
+                    const int32_t nb = i < deg ? list[i] : -1;
+                    bool isnew = false;
+                    if (nb >= 0) isnew = vs.insert((uint32_t) nb, false);
+                    const unsigned nmask = __ballot_sync(FULL, isnew);
+                    if (isnew) cbuf[__popc(nmask & ((1u << lane) - 1u))] = nb;
+                    nnew = __popc(nmask);
+                    vs.added(nnew, false);
+                    ctr.n_dist += nnew;
+                }
+                if (lane == 0) { ctl[1] = nnew; ctl[2] = st; }
+            } else if (warp == 1 && cb == 0 && lc == 0 && deg <= 32) {
+                // look ahead: rows the next expansion will most likely want, into L2 (reads of the visited table race
+                // with warp 0's inserts: a stale answer only costs a useless prefetch)
+                const int nxt = ctl[3];
+                if (nxt >= 0) {
+                    const int32_t nb = lane < deg ? __ldg(g.nbr0 + (size_t) nxt * deg + lane) : -1;
+                    if (nb >= 0 && !vs.contains((uint32_t) nb)) prefetch_l2_bulk(g.vecs + (size_t) nb * g.row_bytes, (uint32_t) g.row_bytes);
+                }
+            }
+            __syncthreads();
+            if (ctl[2] != ST_OK) return ctl[2];
+            const int nnew = ctl[1];
+            // distances: two candidates per warp and pass
+            for (int j0 = warp * 2; j0 < nnew; j0 += CTA_WARPS * 2) {
+                if (j0 + 1 < nnew) {
+                    const int32_t ids[2] = { cbuf[j0], cbuf[j0 + 1] };
+                    const float sd = group_distance<T, IP, NV, 2>(g.vecs, (uint32_t) g.row_bytes, g.nvec, q, ids, lane);
+                    const float v1 = __shfl_sync(FULL, sd, 16);
+                    if (lane == 0) { dbuf[j0] = sd; dbuf[j0 + 1] = v1; }
+                } else {
+                    const int32_t ids[1] = { cbuf[j0] };
+                    const float sd = group_distance<T, IP, NV, 1>(g.vecs, (uint32_t) g.row_bytes, g.nvec, q, ids, lane);
+                    if (lane == 0) dbuf[j0] = sd;
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                int st = ST_OK;
+                for (int j = 0; j < nnew && st == ST_OK; j++) {
+                    const float ed = dbuf[j];
+                    const uint32_t eid = (uint32_t) cbuf[j];
+                    if (w.L >= ef && !(ed < w.d[ef - 1])) continue;
+                    st = wlist_insert(w, ed, eid, ef, lane, low, nd);
+                }
+                if (lane == 0) ctl[2] = st;
+            }
+            __syncthreads();
+            if (ctl[2] != ST_OK) return ctl[2];
+        }
+    }
+    return ST_OK;
+}
+
+template <typename T, int IP, int NV>
+__global__ void __launch_bounds__(CTA_WARPS * 32, 1) scan_cta_kernel(const ScanParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const GraphView &g = p.g;
+    float *q = reinterpret_cast<float *>(smem);
+    unsigned char *s = smem + (size_t) g.nvec * Vec<T>::VEC * 4;
+    WList w;
+    w.d = reinterpret_cast<float *>(s);
+    w.id = reinterpret_cast<uint32_t *>(s + (size_t) p.capW * 4);
+    w.cap = p.capW;
+    VisitedHash vs;
+    vs.tab = reinterpret_cast<uint32_t *>(s + (size_t) p.capW * 8);
+    vs.set_overflow(nullptr, 0);
+    int32_t *cbuf = reinterpret_cast<int32_t *>(vs.tab + CTA_SLOTS);
+    float *dbuf = reinterpret_cast<float *>(cbuf + 64);
+    volatile int *ctl = reinterpret_cast<volatile int *>(dbuf + 64);
+
+    for (int64_t qi = blockIdx.x; qi < p.nq; qi += gridDim.x) {
+        __syncthreads();
+        // every warp stages the query (same values): no barrier needed before each warp's own reads... but the other
+        // warps read it too, so stage once and synchronise
+        if (warp == 0) stage_query<T>(reinterpret_cast<const T *>(p.queries) + qi * g.dim, g.dim, g.nvec, q, lane);
+        __syncthreads();
+        QueryCounters ctr = { 0, 0, 0 };
+        int st = ST_OK;
+        w.L = 0;
+        if (g.entry >= 0) {
+            if (warp == 0) {
+                const float d0 = one_distance<T, IP, NV>(g, q, g.entry, lane);
+                ctr.n_dist = 1;
+                if (lane == 0) { w.d[0] = d0; w.id[0] = (uint32_t) g.entry; }
+            }
+            w.L = 1;
+            for (int lc = g.entry_level; lc >= 0 && st == ST_OK; lc--) {
+                const int ef = lc == 0 ? p.ef : 1;
+                vs.configure(lc == 0 ? CTA_SLOTS : 1024);
+                __syncthreads();
+                if (warp == 0) {
+                    st = wlist_as_entries(w, vs, 1, lane);
+                    if (lane == 0) { ctl[2] = st; ctl[4] = w.L; }
+                }
+                __syncthreads();
+                st = ctl[2];
+                w.L = ctl[4];
+                if (st == ST_OK) st = search_layer_cta<T, IP, NV>(g, w, vs, q, cbuf, dbuf, ctl, ef, lc, lane, warp, ctr);
+                // warp 0 owns the list: its length and the table's fill are what the other warps must agree on next round
+                __syncthreads();
+                if (warp == 0 && lane == 0) { ctl[4] = w.L; ctl[5] = vs.count; }
+                __syncthreads();
+                w.L = ctl[4];
+                vs.count = ctl[5];
+            }
+        }
+        if (st != ST_OK) {
+            if (threadIdx.x == 0) {
+                const int slot = atomicAdd(p.slow_count, 1);
+                p.slow_list[slot] = (int32_t) qi;
+                p.status[qi] = st;
+            }
+            continue;
+        }
+        const int cnt = min(w.L, p.ef);
+        for (int j = threadIdx.x; j < p.out_stride; j += CTA_WARPS * 32) {
+            p.out_elem[qi * p.out_stride + j] = j < cnt ? (int32_t) (w.id[j] & ID_MASK) : -1;
+            p.out_dist[qi * p.out_stride + j] = j < cnt ? w.d[j] : __int_as_float(0x7f800000);
+        }
+        if (threadIdx.x == 0) {
+            p.out_cnt[qi] = cnt;
+            p.status[qi] = 0;
+            atomicAdd(p.totals + 0, (unsigned long long) ctr.n_dist);
+            atomicAdd(p.totals + 1, (unsigned long long) ctr.n_hop0);
+            atomicAdd(p.totals + 2, (unsigned long long) ctr.n_hopu);
+            if (p.per_query) {
+                p.per_query[qi * 4 + 0] = ctr.n_dist;
+                p.per_query[qi * 4 + 1] = ctr.n_hop0;
+                p.per_query[qi * 4 + 2] = ctr.n_hopu;
+                p.per_query[qi * 4 + 3] = 0;
+            }
+        }
+    }
+}
+
+template <typename T, int IP, int NV>
+cudaError_t launch_scan_cta_variant(const ScanParams &p, int num_sms, cudaStream_t stream)
+{
+    auto kern = scan_cta_kernel<T, IP, NV>;
+    const size_t smem = scan_cta_smem<T>(p.g.nvec, p.capW);
+    static thread_local size_t seen[16];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 15;
+    if (seen[dev] != smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return e;
+        seen[dev] = smem;
+    }
+    int grid = (int) (p.nq < (int64_t) num_sms * 2 ? p.nq : (int64_t) num_sms * 2);
+    if (grid < 1) grid = 1;
+    kern<<<grid, CTA_WARPS * 32, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// batches small enough that the GPU is mostly idle: one CTA per query (shared memory must hold the list and the table)
+inline bool use_cta_scan(const ScanParams &p, int num_sms, size_t row_smem_bytes, const void *ep, int variant)
+{
+    if (ep != nullptr || variant == 9 || variant == 6) return false;
+    if (p.nq > num_sms) return false;
+    return row_smem_bytes + (size_t) p.capW * 8 + (size_t) CTA_SLOTS * 4 + 1024 <= 200 * 1024;
+}
+
+template <typename T, int IP>
+cudaError_t launch_scan_cta_t(const ScanParams &p, int num_sms, cudaStream_t stream)
+{
+    switch (nv_of(p.g.nvec)) {
+#define HB_CCASE(NVV, GG, MB) case NVV: return launch_scan_cta_variant<T, IP, NVV>(p, num_sms, stream);
+        HB_NV_TABLE(HB_CCASE)
+#undef HB_CCASE
+    default: return launch_scan_cta_variant<T, IP, 0>(p, num_sms, stream);
+    }
+}
+
+}   // namespace hb
