@@ -233,6 +233,9 @@ inline bool use_cta_scan(const ScanParams &p, int num_sms, size_t row_smem_bytes
 {
     if (ep != nullptr || variant == 9 || variant == 6) return false;
     if (p.nq > num_sms) return false;
+    // measured (profiles/r2_experiments.md): rows of 3 KB gain 15-20 % at 32..148 queries; rows of 512 B lose 15-25 %
+    // to the register-list kernel, whose hop is shorter than this kernel's three block barriers.  variant 7 forces it.
+    if (p.g.nvec < 96 && variant != 7) return false;
     return row_smem_bytes + (size_t) p.capW * 8 + (size_t) CTA_SLOTS * 4 + 1024 <= 200 * 1024;
 }
 

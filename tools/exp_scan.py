@@ -24,6 +24,7 @@ ap.add_argument("--opclass", default="")
 ap.add_argument("--variants", default="0")
 ap.add_argument("--streams", default="1,3")
 ap.add_argument("--latency", action="store_true", help="also time single scans through hb_rescan + hb_gettuple")
+ap.add_argument("--latency-variants", default="", help="variants to repeat the latency loop under (6 = no CTA-per-query kernel)")
 ap.add_argument("--seed", type=int, default=20260103)
 ap.add_argument("--slots", type=int, default=0, help="visited-table slots (0 = automatic)")
 a = ap.parse_args()
@@ -83,7 +84,10 @@ for variant in [int(v) for v in a.variants.split(",")]:
         print("variant=%d streams=%d: %.3f ms/step  %.0f QPS  %.0f GB/s alg (%.3f of 6456)  n_dist/q=%.1f hops/q=%.1f slow=%d recall@10=%.4f"
               % (variant, ns, ms, a.nq / ms * 1e3, alg / ms / 1e6, alg / ms / 1e6 / 6455.9, c["n_dist"] / a.nq / nsteps,
                  (c["n_hop0"] + c["n_hopu"]) / a.nq / nsteps, c["n_slow"], rec), flush=True)
-if a.latency:
+for lv in ([int(v) for v in a.latency_variants.split(",")] if a.latency_variants else [None]) if a.latency else []:
+    if lv is not None:
+        ix.set_option("variant", lv)
+        print("latency under variant %d" % lv, flush=True)
     qh = q_all[1][:200].cpu().numpy()
     sc = ix.beginscan()
     for i in range(20):
@@ -94,9 +98,13 @@ if a.latency:
         sc.rescan(qh[i], a.ef)
         sc.gettuple()
     dt = (time.perf_counter() - t0) / 180
+    sc.endscan()
     print("hb_rescan + first hb_gettuple: %.1f us" % (dt * 1e6), flush=True)
-    for nqs in (1, 8, 64, 512):
+    for nqs in (1, 8, 32, 64, 148, 512):
+        qs = qh[:nqs] if nqs <= 200 else np.tile(qh, (3, 1))[:nqs]
+        for r in range(3):
+            ix.search(qs, 10, a.ef)
         t0 = time.perf_counter()
         for r in range(20):
-            ix.search(qh[:min(nqs, 200)] if nqs <= 200 else np.tile(qh, (3, 1))[:nqs], 10, a.ef)
+            ix.search(qs, 10, a.ef)
         print("hb_search_batch nq=%d: %.1f us" % (nqs, (time.perf_counter() - t0) / 20 * 1e6), flush=True)
