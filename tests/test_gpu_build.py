@@ -123,20 +123,46 @@ def test_batched_build_recall_within_half_point(oracle, pkg, metric, dtype, dim)
     ix.close()
 
 
-def _recall_pair(oracle, pkg, x, q, metric, opclass, efs=(40,)):
-    """recall@10 at each ef_search of the oracle-built graph (sequential pgvector insert loop, natural summation order) and
-    of the GPU-batched-built graph, on the same rows, against the exact answer: {ef: (oracle, gpu)}."""
+def _oracle_built(oracle, x, metric, tag):
+    """the sequentially built graph (pgvector's insert loop restated, natural summation order, single thread).  With
+    HB_ORACLE_GRAPH_CACHE=<dir> the graph of a given (tag, shape) is kept there between runs: the 200k x 768 build
+    takes 4-7 minutes of one core and the generators are deterministic."""
+    import os
     n, dim = x.shape
+    cache = os.environ.get("HB_ORACLE_GRAPH_CACHE")
+    path = os.path.join(cache, "orc_%s_%d_%d.npz" % (tag, n, dim)) if cache else None
+    if path and os.path.exists(path):
+        z = np.load(path)
+        vecs = x if metric != oracle.COSINE else np.stack([oracle.normalize(r, 0, oracle.NATURAL)[0] for r in x])
+        g = oracle.Graph(dim=dim, m=16, efc=64, metric=metric, dtype=0, n=n, upper_rows=int(z["meta"][0]), entry=int(z["meta"][1]),
+                         entry_level=int(z["meta"][2]), vecs=vecs, level=z["level"], nbr0=z["nbr0"], uoff=z["uoff"],
+                         nbru=z["nbru"], ntids=z["ntids"], tids=z["tids"])
+        return oracle.Index.from_graph(g, mode=oracle.NATURAL)
     orc = oracle.Index(dim, 16, 64, metric, 0, oracle.NATURAL, seed=1)
     orc.build(x)
+    if path:
+        g = orc.export()                # the rows are not kept: they are regenerated and normalised again on load
+        np.savez_compressed(path, meta=np.array([g.upper_rows, g.entry, g.entry_level], np.int64), level=g.level, nbr0=g.nbr0,
+                            uoff=g.uoff, nbru=g.nbru, ntids=g.ntids, tids=g.tids)
+    return orc
+
+
+def _recall_pair(oracle, pkg, x, q, metric, opclass, efs=(40,), tag="g"):
+    """recall@10 at each ef_search of the oracle-built graph and of the GPU-batched-built graph, on the same rows, against
+    the exact answer, per query: {ef: (oracle mean, gpu mean, standard error of the paired difference)}.  10 000 queries:
+    with 1000 the paired difference of two equally good graphs scatters by +-0.6 pt, more than the criterion."""
+    n, dim = x.shape
+    orc = _oracle_built(oracle, x, metric, tag)
     ix = pkg.HnswIndex(dim, opclass, 16, 64, capacity=n, seed=1)
     assert ix.build(x) == n
     gt, _ = ix.bruteforce(q, 10)
+    per_query = lambda ids: np.array([len(set(ids[i]) & set(gt[i])) / 10 for i in range(len(gt))])
     out = {}
     for ef in efs:
         oe, _, _, _ = orc.search_batch(q, ef, threads=8)
         ge, _, _ = ix.search_elements(q, ef)
-        out[ef] = (recall(oe[:, :10], gt), recall(ge[:, :10], gt))
+        ro, rg = per_query(oe[:, :10]), per_query(ge[:, :10])
+        out[ef] = (float(ro.mean()), float(rg.mean()), float((rg - ro).std() / np.sqrt(len(gt))))
     ix.close()
     return out
 
@@ -145,26 +171,26 @@ def test_build_recall_at_configs0_size(oracle, pkg):
     """north_star: "a GPU-built graph's recall@10 falls within 0.5 pt of the reference's" -- at the size of configs[0]
     (100k x 128 fp32 L2, m=16, ef_construction=64, ef_search=40).  The oracle build is the slow part (~40 s)."""
     x = sift_like(100000, 128, seed=31)
-    q = sift_like(1000, 128, seed=32)
-    r_o, r_g = _recall_pair(oracle, pkg, x, q, oracle.L2, "vector_l2_ops")[40]
-    print("100k x 128: oracle-built %.4f, GPU-built %.4f" % (r_o, r_g))
-    assert r_g >= r_o - 0.005, (r_g, r_o)
+    q = sift_like(10000, 128, seed=32)
+    r_o, r_g, se = _recall_pair(oracle, pkg, x, q, oracle.L2, "vector_l2_ops", tag="sift")[40]
+    print("100k x 128: oracle-built %.4f, GPU-built %.4f (+- %.4f)" % (r_o, r_g, se))
+    assert r_g >= r_o - 0.005, (r_g, r_o, se)
 
 
 @pytest.mark.parametrize("n", [30000] + ([200000] if __import__("os").environ.get("HB_SLOW_TESTS") else []))
 def test_build_recall_768_cosine(oracle, pkg, n):
     """the same criterion on configs[1]-shaped rows (768-d cosine).  30k rows in the default suite; HB_SLOW_TESTS=1 adds
-    200k rows (a ~4 minute single-threaded oracle build).  Measured at 200k (profiles/r2_build_recall_200k.txt): equal
-    at ef_search=100 (0.9618 vs 0.9616) but 0.8 pt BELOW the oracle-built graph at ef_search=40 (0.907 vs 0.915), whatever
-    the batch fraction -- elements of one batch (4 % of the graph) do not see each other.  That misses north_star's 0.5 pt at
-    that operating point; the assertion below is the criterion at ef_search=100 and a 1-pt bound at 40, and DESIGN.md says so."""
+    200k rows (a 4-7 minute single-threaded oracle build).  Measured at 200k over 10 000 queries
+    (profiles/r2_build_recall_200k.txt): paired difference GPU-built minus oracle-built -0.12 +- 0.18 pt at ef_search=40
+    and +0.08 +- 0.16 pt at 100 -- the 0.8 pt an earlier 1000-query run showed was sampling scatter."""
     x = clustered(n, 768, 256, seed=33)
-    q = clustered(1000, 768, 256, seed=34)
-    res = _recall_pair(oracle, pkg, x, q, oracle.COSINE, "vector_cosine_ops", efs=(40, 100))
-    for ef, (r_o, r_g) in res.items():
-        print("%d x 768 cosine, ef_search=%d: oracle-built %.4f, GPU-built %.4f" % (n, ef, r_o, r_g))
-    assert res[100][1] >= res[100][0] - 0.005, res
-    assert res[40][1] >= res[40][0] - (0.005 if n <= 30000 else 0.01), res
+    q = clustered(10000, 768, 256, seed=34)
+    res = _recall_pair(oracle, pkg, x, q, oracle.COSINE, "vector_cosine_ops", efs=(40, 100), tag="clu")
+    for ef, (r_o, r_g, se) in res.items():
+        print("%d x 768 cosine, ef_search=%d: oracle-built %.4f, GPU-built %.4f (+- %.4f)" % (n, ef, r_o, r_g, se))
+    for ef in (40, 100):
+        assert res[ef][1] >= res[ef][0] - 0.005, res
+
 
 def test_build_is_deterministic(pkg):
     x = clustered(5000, 48, 32, seed=6)

@@ -1,5 +1,6 @@
 """north_star's build criterion at size: recall@10 of the oracle-built graph (sequential pgvector insert loop, natural
 summation order) vs GPU-built graphs under different batch fractions, same rows, same queries, exact ground truth.
+NOTE: 1000 queries scatter by +-0.6 pt in the paired difference; tools/exp_build_recall2.py is the 10 000-query form.
 usage: python tools/exp_build_recall.py n dim [ef]   (the oracle build is single-threaded: ~4 min at 200000 x 768)"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
