@@ -128,7 +128,14 @@ template <int VEC> __device__ __forceinline__ float fold_lane2(const f32x2 (&p)[
 // NV > 0: the row is exactly 32*NV chunks (every lane owns NV chunks; loads are issued
 // back-to-back from one base pointer per row with immediate offsets, G*NV 128-bit loads in flight
 // per lane); NV == 0: run-time loop for any row length.
-template <typename T, int IP, int NV, int G>
+// SMEM: `vecs` is an array of rows staged in shared memory and ids are its slot numbers (same arithmetic, other loads).
+template <bool SMEM> __device__ __forceinline__ uint4 ld_row_chunk(const void *p)
+{
+    if constexpr (SMEM) return *reinterpret_cast<const uint4 *>(p);
+    else return ldg_stream(p);
+}
+
+template <typename T, int IP, int NV, int G, bool SMEM = false>
 __device__ __forceinline__ void group_partials(const char *__restrict__ vecs, uint32_t row_bytes, int nvec,
                                                const float *q, const int32_t (&ids)[G], int lane,
                                                float (&part)[G])
@@ -152,7 +159,7 @@ __device__ __forceinline__ void group_partials(const char *__restrict__ vecs, ui
 #pragma unroll
         for (int c = 0; c < G; c++)
 #pragma unroll
-            for (int j = 0; j < NV; j++) raw[c][j] = ldg_stream(rp[c] + 512 * j);
+            for (int j = 0; j < NV; j++) raw[c][j] = ld_row_chunk<SMEM>(rp[c] + 512 * j);
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             const float4 qa = *reinterpret_cast<const float4 *>(qp + 128 * j);
@@ -166,7 +173,7 @@ __device__ __forceinline__ void group_partials(const char *__restrict__ vecs, ui
         for (int ch = lane; ch < nvec; ch += 32) {
             uint4 raw[G];
 #pragma unroll
-            for (int c = 0; c < G; c++) raw[c] = ldg_stream(rp[c] + 16 * (ch - lane));
+            for (int c = 0; c < G; c++) raw[c] = ld_row_chunk<SMEM>(rp[c] + 16 * (ch - lane));
             const float4 qa = *reinterpret_cast<const float4 *>(q + 4 * ch);
             float4 qb = qa;
             if constexpr (HALF) qb = *reinterpret_cast<const float4 *>(q + plane + 4 * ch);
@@ -206,12 +213,12 @@ template <> struct XReduce<1> {
 };
 
 // distances of G candidates; result of candidate c is returned in every lane via out[c]
-template <typename T, int IP, int NV, int G>
+template <typename T, int IP, int NV, int G, bool SMEM = false>
 __device__ __forceinline__ float group_distance(const char *__restrict__ vecs, uint32_t row_bytes, int nvec,
                                                 const float *q, const int32_t (&ids)[G], int lane)
 {
     float part[G];
-    group_partials<T, IP, NV, G>(vecs, row_bytes, nvec, q, ids, lane, part);
+    group_partials<T, IP, NV, G, SMEM>(vecs, row_bytes, nvec, q, ids, lane, part);
     const float s = XReduce<G>::run(part, lane, 16);
     return IP == 1 ? -s : s;   // lane (c * 32/G) .. hold candidate c
 }

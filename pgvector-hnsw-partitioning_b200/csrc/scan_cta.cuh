@@ -15,8 +15,22 @@
 // Queries whose tie tail or visited set outgrow shared memory go to the large-visited-set path like everywhere else.
 #pragma once
 #include "scan_kernel.cuh"
+#include "scan_reg.cuh"
 
 namespace hb {
+
+// -DHB_CTA_PROFILE: cycles of warp 0 per phase of an expansion, printed per layer-0 search (experiments only)
+#ifdef HB_CTA_PROFILE
+#define HB_CTA_PROF_DECL long long pt_[5] = { 0, 0, 0, 0, 0 }, pl_ = clock64(); int phit_ = 0, pn_ = 0, pprev_ = -2;
+#define HB_CTA_PROF_MARK(k) { const long long t_ = clock64(); pt_[k] += t_ - pl_; pl_ = t_; }
+#define HB_CTA_PROF_PRED(cid, nxt) { if (cid >= 0) { pn_++; phit_ += (cid == pprev_); } pprev_ = nxt; }
+#define HB_CTA_PROF_DUMP if (threadIdx.x == 0 && lc == 0 && blockIdx.x == 0) printf("cta prof: hops %d predicted %d; cycles pick %lld list+filter %lld distances %lld insert %lld loop %lld\n", pn_, phit_, pt_[0], pt_[1], pt_[2], pt_[3], pt_[4]);
+#else
+#define HB_CTA_PROF_DECL
+#define HB_CTA_PROF_MARK(k)
+#define HB_CTA_PROF_PRED(cid, nxt)
+#define HB_CTA_PROF_DUMP
+#endif
 
 constexpr int CTA_WARPS = 4;
 constexpr int CTA_SLOTS = 8192;          // visited table of the layer-0 search (32 kB: one CTA per SM is plenty)
@@ -37,7 +51,9 @@ __device__ __forceinline__ int search_layer_cta(const GraphView &g, WList &w, Vi
     const int deg = lc == 0 ? 2 * g.m : g.m;
     int low = 0;                       // warp 0 only
     NoDiscard nd;
+    HB_CTA_PROF_DECL
     for (;;) {
+        HB_CTA_PROF_MARK(4)
         if (warp == 0) {
             int idx = -1, nxt = -1;
             for (int base = low; base < w.L && idx < 0; base += 32) {
@@ -57,9 +73,11 @@ __device__ __forceinline__ int search_layer_cta(const GraphView &g, WList &w, Vi
                 low = idx + 1;
                 if (lc == 0) ctr.n_hop0++; else ctr.n_hopu++;
             }
+            HB_CTA_PROF_PRED(cid, nxt)
             if (lane == 0) { ctl[0] = cid; ctl[3] = nxt; ctl[1] = 0; }
         }
         __syncthreads();
+        HB_CTA_PROF_MARK(0)
         const int cid = ctl[0];
         if (cid < 0) break;
         const int32_t *list = lc == 0 ? g.nbr0 + (size_t) cid * deg : g.nbru + ((size_t) g.uoff[cid] + (lc - 1)) * g.m;
@@ -91,6 +109,7 @@ __device__ __forceinline__ int search_layer_cta(const GraphView &g, WList &w, Vi
                 }
             }
             __syncthreads();
+            HB_CTA_PROF_MARK(1)
             if (ctl[2] != ST_OK) return ctl[2];
             const int nnew = ctl[1];
             // distances: two candidates per warp and pass
@@ -107,6 +126,7 @@ __device__ __forceinline__ int search_layer_cta(const GraphView &g, WList &w, Vi
                 }
             }
             __syncthreads();
+            HB_CTA_PROF_MARK(2)
             if (warp == 0) {
                 int st = ST_OK;
                 for (int j = 0; j < nnew && st == ST_OK; j++) {
@@ -118,9 +138,11 @@ __device__ __forceinline__ int search_layer_cta(const GraphView &g, WList &w, Vi
                 if (lane == 0) ctl[2] = st;
             }
             __syncthreads();
+            HB_CTA_PROF_MARK(3)
             if (ctl[2] != ST_OK) return ctl[2];
         }
     }
+    HB_CTA_PROF_DUMP
     return ST_OK;
 }
 
@@ -208,22 +230,330 @@ __global__ void __launch_bounds__(CTA_WARPS * 32, 1) scan_cta_kernel(const ScanP
     }
 }
 
+// ---- the same, with the list in warp 0's registers and one expansion of look-ahead staged in shared memory ----------
+// (ef + room for the tie tail <= 128 entries: scan_reg.cuh's RegW<4>.)  What a single scan waits for is, per expansion,
+// a neighbour-list read, a row gather and the insertions.  Here warp 1 reads the list of the entry that will be expanded
+// NEXT while the current rows are evaluated, and -- once the current distances are known and none of them overtakes that
+// entry -- copies the rows of its not-yet-visited neighbours into shared memory (cp.async.bulk, one mbarrier phase per
+// expansion), so that the next expansion finds its list and its rows on chip.  Only the source of the bytes changes: the
+// expansion order, the per-row summation order and therefore ids, distances and counters are those of every other kernel.
+struct CtaSmem {
+    int32_t *cbuf, *cslot, *nlist;      // new candidates (ids | positions in the list) | the next expansion's list
+    float *dbuf;
+    volatile int *ctl;                  // 0 cid | 1 nnew | 2 status | 3 next | 5 rows staged | 6 list tag | 8 row tag | 9 parity | 11 next's distance
+    uint64_t *mbar;
+    char *rows;                         // 32 x row_bytes (row staging enabled) or nullptr
+};
+
+struct CtaLook { uint32_t issued; bool pending; };       // warp 1: row batches issued, last one not yet seen complete
+
+__device__ __forceinline__ uint32_t cta_smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cta_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    // bounded: a protocol error must end the kernel with an error, not hang the device
+    for (int spin = 0; spin < (1 << 22); spin++) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(cta_smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+template <typename T> __host__ __device__ inline size_t scan_cta_reg_smem(int nvec, size_t row_bytes, bool stage_rows)
+{
+    // query | visited table | cbuf, cslot, nlist, dbuf (32 words each) | control words | mbarrier | staged rows
+    return (((size_t) nvec * Vec<T>::VEC * 4 + (size_t) CTA_SLOTS * 4 + 4 * 128 + 64 + 16 + (stage_rows ? 32 * row_bytes : 0)) + 15) & ~(size_t) 15;
+}
+
+template <typename T, int IP, int NV, int R>
+__device__ __forceinline__ int search_layer_cta_reg(const GraphView &g, RegW<R> &w, VisitedHash &vs, const float *q,
+                                                    const CtaSmem &S, int ef, int lc, int lane, int warp,
+                                                    QueryCounters &ctr, CtaLook &lk)
+{
+    const int deg = lc == 0 ? 2 * g.m : g.m;
+    const bool look = lc == 0 && deg <= 32;         // look-ahead: layer 0, lists of one chunk
+    const uint32_t row_bytes = (uint32_t) g.row_bytes;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    volatile int *ctl = S.ctl;
+    if (threadIdx.x == 0) { ctl[6] = -1; ctl[8] = -1; }        // nothing staged yet (read after the first barrier below)
+    HB_CTA_PROF_DECL
+    for (;;) {
+        HB_CTA_PROF_MARK(4)
+        if (warp == 0) {
+            // nearest unexpanded entry, and the one after it
+            int mys = 0x7fffffff, mys2 = 0x7fffffff;
+#pragma unroll
+            for (int r = R - 1; r >= 0; r--)
+                if (!(w.id[r] & EXP_BIT)) { mys2 = mys; mys = lane * R + r; }
+            const unsigned b = __ballot_sync(FULL, mys != 0x7fffffff);
+            int cid = -1, nxt = -1;
+            float nxd = 0.f;
+            if (b) {
+                const int src = __ffs(b) - 1;
+                const int idx = __shfl_sync(FULL, mys, src);
+                cid = (int) __shfl_sync(FULL, RegW<R>::pick(w.id, mys), src);
+                int idx2 = __shfl_sync(FULL, mys2, src);
+                const unsigned b2 = b & (b - 1);
+                if (b2) idx2 = min(idx2, __shfl_sync(FULL, mys, __ffs(b2) - 1));
+                if (look && idx2 != 0x7fffffff) { nxt = (int) w.get_id(idx2); nxd = w.get_d(idx2); }
+#pragma unroll
+                for (int r = 0; r < R; r++) if (lane * R + r == idx) w.id[r] |= EXP_BIT;
+                if (lc == 0) ctr.n_hop0++; else ctr.n_hopu++;
+            }
+            HB_CTA_PROF_PRED(cid, nxt)
+            if (lane == 0) { ctl[0] = cid; ctl[3] = nxt; ctl[11] = __float_as_int(nxd); ctl[1] = 0; }
+        }
+        __syncthreads();
+        HB_CTA_PROF_MARK(0)
+        const int cid = ctl[0];
+        if (cid < 0) break;
+        const int nxt = ctl[3];
+        const int32_t *list = lc == 0 ? g.nbr0 + (size_t) cid * deg : g.nbru + ((size_t) g.uoff[cid] + (lc - 1)) * g.m;
+        int32_t look_nb = -1;              // warp 1: the next expansion's list, in flight until the distances are done
+        for (int cb = 0; cb < deg; cb += 32) {
+            if (warp == 0) {
+                int st = ST_OK, nnew = 0, staged = 0;
+                if (cb == 0 && !vs.room(deg)) st = ST_TABLE;
+                if (st == ST_OK) {
+                    const int i = cb + lane;
+                    int32_t nb;
+                    if (look && ctl[6] == cid) nb = S.nlist[lane];           // read ahead by the previous expansion
+                    else nb = i < deg ? list[i] : -1;
+                    bool isnew = false;
+                    if (nb >= 0) isnew = vs.insert((uint32_t) nb, false);
+                    const unsigned nmask = __ballot_sync(FULL, isnew);
+                    if (isnew) {
+                        const int j = __popc(nmask & lt_mask);
+                        S.cbuf[j] = nb;
+                        S.cslot[j] = lane;
+                    }
+                    nnew = __popc(nmask);
+                    vs.added(nnew, false);
+                    ctr.n_dist += nnew;
+                    staged = look && ctl[8] == cid;
+                }
+                if (lane == 0) { ctl[1] = nnew; ctl[2] = st; ctl[5] = staged; }
+            } else if (warp == 1 && look && nxt >= 0) {
+                look_nb = lane < deg ? __ldg(g.nbr0 + (size_t) nxt * deg + lane) : -1;
+            }
+            __syncthreads();
+            HB_CTA_PROF_MARK(1)
+            if (ctl[2] != ST_OK) return ctl[2];
+            const int nnew = ctl[1];
+            const bool staged = ctl[5] != 0;
+            // distances: two candidates per warp and pass; the rows come from shared memory when they were staged
+            if (staged && warp * 2 < nnew) cta_mbar_wait(S.mbar, (uint32_t) ctl[9]);
+            for (int j0 = warp * 2; j0 < nnew; j0 += CTA_WARPS * 2) {
+                if (j0 + 1 < nnew) {
+                    float sd;
+                    if (staged) {
+                        const int32_t ids[2] = { S.cslot[j0], S.cslot[j0 + 1] };
+                        sd = group_distance<T, IP, NV, 2, true>(S.rows, row_bytes, g.nvec, q, ids, lane);
+                    } else {
+                        const int32_t ids[2] = { S.cbuf[j0], S.cbuf[j0 + 1] };
+                        sd = group_distance<T, IP, NV, 2>(g.vecs, row_bytes, g.nvec, q, ids, lane);
+                    }
+                    const float v1 = __shfl_sync(FULL, sd, 16);
+                    if (lane == 0) { S.dbuf[j0] = sd; S.dbuf[j0 + 1] = v1; }
+                } else {
+                    float sd;
+                    if (staged) {
+                        const int32_t ids[1] = { S.cslot[j0] };
+                        sd = group_distance<T, IP, NV, 1, true>(S.rows, row_bytes, g.nvec, q, ids, lane);
+                    } else {
+                        const int32_t ids[1] = { S.cbuf[j0] };
+                        sd = group_distance<T, IP, NV, 1>(g.vecs, row_bytes, g.nvec, q, ids, lane);
+                    }
+                    if (lane == 0) S.dbuf[j0] = sd;
+                }
+            }
+            if (warp == 1 && look && cb == 0) {
+                S.nlist[lane] = look_nb;
+                if (lane == 0) ctl[6] = nxt;
+            }
+            __syncthreads();
+            HB_CTA_PROF_MARK(2)
+            if (warp == 0) {
+                // admit and insert in neighbour order, as the sequential loop does
+                const float myd = lane < nnew ? S.dbuf[lane] : __int_as_float(0x7f800000);
+                const uint32_t cj = lane < nnew ? (uint32_t) S.cbuf[lane] : 0u;
+                unsigned amask = __ballot_sync(FULL, lane < nnew && (w.L < ef || myd < w.f));
+                int st = ST_OK;
+                while (amask && st == ST_OK) {
+                    const int sl = __ffs(amask) - 1;
+                    amask &= amask - 1;
+                    const float ed = __shfl_sync(FULL, myd, sl);
+                    const uint32_t eid = __shfl_sync(FULL, cj, sl);
+                    if (w.L >= ef && !(ed < w.f)) continue;
+                    st = w.insert(ed, eid, ef, lane);
+                }
+                if (lane == 0) ctl[2] = st;
+            } else if (warp == 1 && look && cb == 0 && S.rows != nullptr) {
+                // stage the rows of the expansion that follows -- unless a candidate just evaluated will be expanded first
+                bool go = nxt >= 0;
+                if (go) {
+                    const float nxd = __int_as_float(ctl[11]);
+                    const float myd = lane < nnew ? S.dbuf[lane] : __int_as_float(0x7f800000);
+                    const bool first = lane < nnew && (myd < nxd || (myd == nxd && (uint32_t) S.cbuf[lane] < (uint32_t) nxt));
+                    go = !__any_sync(FULL, first);
+                }
+                if (go) {
+                    const bool need = look_nb >= 0 && !vs.contains((uint32_t) look_nb);
+                    const int cnt = __popc(__ballot_sync(FULL, need));
+                    if (cnt) {
+                        if (lk.pending) { cta_mbar_wait(S.mbar, (lk.issued - 1u) & 1u); lk.pending = false; }
+                        if (lane == 0) {
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                                         ::"r"(cta_smem_u32(S.mbar)), "r"((uint32_t) cnt * row_bytes) : "memory");
+                        }
+                        __syncwarp();
+                        if (need)
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                         ::"r"(cta_smem_u32(S.rows + (size_t) lane * row_bytes)),
+                                           "l"(g.vecs + (size_t) (uint32_t) look_nb * row_bytes), "r"(row_bytes),
+                                           "r"(cta_smem_u32(S.mbar)) : "memory");
+                        if (lane == 0) ctl[9] = (int) (lk.issued & 1u);
+                        lk.issued++;
+                        lk.pending = true;
+                    }
+                    if (lane == 0) ctl[8] = nxt;
+                } else if (lane == 0) ctl[8] = -1;
+            }
+            __syncthreads();
+            HB_CTA_PROF_MARK(3)
+            if (ctl[2] != ST_OK) return ctl[2];
+        }
+    }
+    HB_CTA_PROF_DUMP
+    return ST_OK;
+}
+
+template <typename T, int IP, int NV, int R>
+__global__ void __launch_bounds__(CTA_WARPS * 32, 1) scan_cta_reg_kernel(const ScanParams p, int stage_rows)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const GraphView &g = p.g;
+    float *q = reinterpret_cast<float *>(smem);
+    VisitedHash vs;
+    vs.tab = reinterpret_cast<uint32_t *>(smem + (size_t) g.nvec * Vec<T>::VEC * 4);
+    vs.set_overflow(nullptr, 0);
+    CtaSmem S;
+    S.cbuf = reinterpret_cast<int32_t *>(vs.tab + CTA_SLOTS);
+    S.cslot = S.cbuf + 32;
+    S.nlist = S.cslot + 32;
+    S.dbuf = reinterpret_cast<float *>(S.nlist + 32);
+    S.ctl = reinterpret_cast<volatile int *>(S.dbuf + 32);
+    S.mbar = reinterpret_cast<uint64_t *>(const_cast<int *>(S.ctl) + 16);
+    S.rows = stage_rows ? reinterpret_cast<char *>(S.mbar + 2) : nullptr;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cta_smem_u32(S.mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    RegW<R> w;                          // warp 0's; the other warps never read theirs
+    CtaLook lk = { 0u, false };
+    const int ef = p.ef;
+
+    for (int64_t qi = blockIdx.x; qi < p.nq; qi += gridDim.x) {
+        __syncthreads();
+        if (warp == 0) stage_query<T>(reinterpret_cast<const T *>(p.queries) + qi * g.dim, g.dim, g.nvec, q, lane);
+        __syncthreads();
+        QueryCounters ctr = { 0, 0, 0 };
+        int st = ST_OK;
+        w.reset();
+        if (g.entry >= 0) {
+            if (warp == 0) {
+                const float d0 = one_distance<T, IP, NV>(g, q, g.entry, lane);
+                ctr.n_dist = 1;
+                if (lane == 0) { w.d[0] = d0; w.id[0] = (uint32_t) g.entry; }
+                w.L = 1;
+            }
+            for (int lc = g.entry_level; lc >= 0 && st == ST_OK; lc--) {
+                const int efl = lc == 0 ? ef : 1;
+                vs.configure(lc == 0 ? CTA_SLOTS : 1024);
+                __syncthreads();                       // nobody still reads the previous layer's table
+                if (warp == 0) {
+                    st = regw_as_entry(w, vs, efl, lane);
+                    if (lane == 0) S.ctl[2] = st;
+                }
+                __syncthreads();
+                st = S.ctl[2];
+                if (st == ST_OK) st = search_layer_cta_reg<T, IP, NV, R>(g, w, vs, q, S, efl, lc, lane, warp, ctr, lk);
+            }
+        }
+        if (st != ST_OK) {
+            if (threadIdx.x == 0) {
+                const int slot = atomicAdd(p.slow_count, 1);
+                p.slow_list[slot] = (int32_t) qi;
+                p.status[qi] = st;
+            }
+            continue;
+        }
+        if (warp == 0) {
+            const int cnt = min(w.L, ef);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int s = lane * R + r;
+                if (s < p.out_stride) {
+                    p.out_elem[qi * p.out_stride + s] = s < cnt ? (int32_t) (w.id[r] & ID_MASK) : -1;
+                    p.out_dist[qi * p.out_stride + s] = s < cnt ? w.d[r] : __int_as_float(0x7f800000);
+                }
+            }
+            if (lane == 0) {
+                p.out_cnt[qi] = cnt;
+                p.status[qi] = 0;
+                atomicAdd(p.totals + 0, (unsigned long long) ctr.n_dist);
+                atomicAdd(p.totals + 1, (unsigned long long) ctr.n_hop0);
+                atomicAdd(p.totals + 2, (unsigned long long) ctr.n_hopu);
+                if (p.per_query) {
+                    p.per_query[qi * 4 + 0] = ctr.n_dist;
+                    p.per_query[qi * 4 + 1] = ctr.n_hop0;
+                    p.per_query[qi * 4 + 2] = ctr.n_hopu;
+                    p.per_query[qi * 4 + 3] = 0;
+                }
+            }
+        }
+    }
+    // no copy may still be in flight towards this CTA's shared memory when it exits
+    if (warp == 1 && lk.pending) cta_mbar_wait(S.mbar, (lk.issued - 1u) & 1u);
+}
+
 template <typename T, int IP, int NV>
 cudaError_t launch_scan_cta_variant(const ScanParams &p, int num_sms, cudaStream_t stream)
 {
-    auto kern = scan_cta_kernel<T, IP, NV>;
-    const size_t smem = scan_cta_smem<T>(p.g.nvec, p.capW);
-    static thread_local size_t seen[16];
+    int grid = (int) (p.nq < (int64_t) num_sms * 2 ? p.nq : (int64_t) num_sms * 2);
+    if (grid < 1) grid = 1;
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 15;
-    if (seen[dev] != smem) {
+    const int sub = p.variant / 10;                   // experiments: 1 = list in shared memory, 2 = no row staging
+    if (sub != 1 && p.ef + 24 <= 128 && p.out_stride <= 128) {
+        auto kern = scan_cta_reg_kernel<T, IP, NV, 4>;
+        const bool stage = sub != 2 && 2 * p.g.m <= 32 && scan_cta_reg_smem<T>(p.g.nvec, p.g.row_bytes, true) <= 200 * 1024;
+        const size_t smem = scan_cta_reg_smem<T>(p.g.nvec, p.g.row_bytes, stage);
+        static thread_local size_t seen_reg[16];
+        if (seen_reg[dev] < smem) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            if (e != cudaSuccess) return e;
+            seen_reg[dev] = smem;
+        }
+        kern<<<grid, CTA_WARPS * 32, smem, stream>>>(p, stage ? 1 : 0);
+        return cudaGetLastError();
+    }
+    auto kern = scan_cta_kernel<T, IP, NV>;
+    const size_t smem = scan_cta_smem<T>(p.g.nvec, p.capW);
+    static thread_local size_t seen[16];
+    if (seen[dev] < smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (e != cudaSuccess) return e;
         seen[dev] = smem;
     }
-    int grid = (int) (p.nq < (int64_t) num_sms * 2 ? p.nq : (int64_t) num_sms * 2);
-    if (grid < 1) grid = 1;
     kern<<<grid, CTA_WARPS * 32, smem, stream>>>(p);
     return cudaGetLastError();
 }
@@ -233,9 +563,10 @@ inline bool use_cta_scan(const ScanParams &p, int num_sms, size_t row_smem_bytes
 {
     if (ep != nullptr || variant == 9 || variant == 6) return false;
     if (p.nq > num_sms) return false;
+    const bool forced = variant % 10 == 7;
     // measured (profiles/r2_experiments.md): rows of 3 KB gain 15-20 % at 32..148 queries; rows of 512 B lose 15-25 %
     // to the register-list kernel, whose hop is shorter than this kernel's three block barriers.  variant 7 forces it.
-    if (p.g.nvec < 96 && variant != 7) return false;
+    if (p.g.nvec < 96 && !forced) return false;
     return row_smem_bytes + (size_t) p.capW * 8 + (size_t) CTA_SLOTS * 4 + 1024 <= 200 * 1024;
 }
 

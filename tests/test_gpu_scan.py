@@ -375,8 +375,10 @@ def test_register_list_tail_and_table_overflow(oracle, pkg):
 @pytest.mark.parametrize("dim,dtype,metric,m,ef", [
     (128, 0, 0, 16, 40), (96, 0, 2, 16, 64), (768, 0, 2, 16, 90), (256, 1, 1, 12, 200), (48, 1, 0, 8, 30), (384, 0, 0, 24, 100)])
 def test_cta_per_query_scan(oracle, pkg, dim, dtype, metric, m, ef):
-    """Small batches of long rows take the four-warps-per-query kernel on their own (>= 1536-byte rows); variant 7
-    forces it for every shape, variant 6 forbids it.  Both must equal the oracle bit for bit, counters included."""
+    """Small batches of long rows take the four-warps-per-query kernels on their own (>= 1536-byte rows); variant 7
+    forces them for every shape (register list + look-ahead row staging when ef <= 104, shared-memory list above), 17
+    forces the shared-memory list, 27 the register list without row staging, 6 forbids the CTA kernels.  All must
+    equal the oracle bit for bit, counters included."""
     dt = np.float16 if dtype else np.float32
     x = sift_like(5000, dim, seed=dim + ef + 7).astype(dt)
     q = sift_like(100, dim, seed=dim + ef + 8).astype(dt)
@@ -386,9 +388,10 @@ def test_cta_per_query_scan(oracle, pkg, dim, dtype, metric, m, ef):
     e1, d1, c1 = ix.search_elements(q, ef)
     e3, d3, c3 = ix.search_elements(q[:1], ef)                     # a single scan
     assert (e3[0] == e1[0]).all() and c3[0] == c1[0]
-    ix.set_option("variant", 6)
-    e2, d2, c2 = ix.search_elements(q, ef)
-    assert (e1 == e2).all() and (d1.view(np.uint32) == d2.view(np.uint32)).all() and (c1 == c2).all()
+    for v in (17, 27, 6):
+        ix.set_option("variant", v)
+        e2, d2, c2 = ix.search_elements(q, ef)
+        assert (e1 == e2).all() and (d1.view(np.uint32) == d2.view(np.uint32)).all() and (c1 == c2).all(), v
     ix.close()
 
 
@@ -401,7 +404,8 @@ def test_cta_per_query_tie_tail(oracle, pkg):
     x[:, :12] = lat
     q = x[rng.integers(0, 4096, 60)]
     orc, ix = make(oracle, pkg, x, oracle.L2, m=8, efc=32)
-    ix.set_option("variant", 7)
-    check_scan(oracle, orc, ix, q, 48, natural_check=False)
-    check_scan(oracle, orc, ix, q, 10, natural_check=False)
+    for v in (7, 17, 27):
+        ix.set_option("variant", v)
+        check_scan(oracle, orc, ix, q, 48, natural_check=False)
+        check_scan(oracle, orc, ix, q, 10, natural_check=False)
     ix.close()
