@@ -691,7 +691,9 @@ def run_partitioned(args, ctx, n, dim):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    run(0, warmup)
+    # every slot in flight is warmed (its buffers are sized on first use): with fewer warm-up steps than slots a
+    # cudaMalloc would land inside the timed region
+    run(0, max(warmup, min(NSLOT, total_steps)))
     pix.counters(reset=True)
     barrier()
     # the library runs on its own streams; the device is idle at both records, so the events bracket the steps
@@ -718,7 +720,7 @@ def run_partitioned(args, ctx, n, dim):
         for slot in range(NSLOT):
             pix.search_wait(slot)
 
-    run_e2e(0, warmup)
+    run_e2e(0, max(warmup, min(NSLOT, total_steps)))
     barrier()
     t0 = time.perf_counter()
     run_e2e(warmup, steps)

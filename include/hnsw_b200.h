@@ -103,7 +103,7 @@ int64_t hb_vacuum_repair(hb_index *ix, int64_t *repaired);
  * element at m = 16 --, batch workspaces), as pgvector frees its in-memory build state when CREATE
  * INDEX ends.  Scans are unaffected; a later hb_insert allocates what it needs again. */
 int hb_index_trim(hb_index *ix);
-/* largest batch of the GPU insert pipeline (0 = automatic: n/16, at most 8192, 16384 from 512k elements; 1 = the sequential
+/* largest batch of the GPU insert pipeline (0 = automatic: n/16, at most 8192; 1 = the sequential
  * algorithm, graph identical to one-at-a-time insertion) */
 int hb_set_build_batch(hb_index *ix, int max_batch);
 /* HnswInitElement's level draw for the seq-th initialised element: (int)(-ln(U) / ln(m)), capped */

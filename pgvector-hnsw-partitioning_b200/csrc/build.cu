@@ -358,10 +358,10 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
     double t_dev[4] = { 0, 0, 0, 0 };   // upload+search | select | commit+edges+sort | link
     if (trace) for (auto &e : tev) HB_CK(cudaEventCreate(&e));
 
-    // automatic batch cap: 8192, and 16384 once the graph holds 512k elements (a batch is then <= 1/32
-    // of it); measured at 1M x 768: the candidate search loses less to its tail, recall@10 unchanged
-    const int max_batch = std::min(ix->opt_build_batch > 0 ? ix->opt_build_batch : 16384, 1 << LINK_KEY_SRC_BITS);
-    const bool auto_batch = ix->opt_build_batch <= 0;
+    // automatic batch cap: 8192 rows.  16384 once the graph holds 512k elements built 1M x 768 4 % faster but cost recall
+    // against the sequentially built graph (10 000 queries, paired: -0.56 / -0.69 pt at ef_search 40 / 90 with 16384,
+    // -0.30 / -0.39 pt with 8192; smaller caps bring nothing more: profiles/r2_build_recall_1m.txt)
+    const int max_batch = std::min(ix->opt_build_batch > 0 ? ix->opt_build_batch : 8192, 1 << LINK_KEY_SRC_BITS);
     int64_t indexed = 0;
     size_t pos = 0;
     std::vector<char> stage, pack;
@@ -456,7 +456,7 @@ int64_t build_insert(hb_index *ix, const void *host_vecs, int64_t n_in, const in
         // such graphs is insensitive to it: profiles/r2_experiments.md), 1/16 otherwise
         const int frac_small = ix->opt_build_fraction_small > 0 ? ix->opt_build_fraction_small : (final_size < 262144 ? 8 : ix->opt_build_fraction);
         const int frac = cur < 65536 ? std::max(2, frac_small) : std::max(2, ix->opt_build_fraction);
-        int64_t b = std::max<int64_t>(1, std::min<int64_t>(auto_batch && cur < 524288 ? 8192 : max_batch, cur / frac));
+        int64_t b = std::max<int64_t>(1, std::min<int64_t>(max_batch, cur / frac));
         b = std::min<int64_t>(b, (int64_t) todo.size() - pos);
         levels.resize(b);
         for (int64_t i = 0; i < b; i++) levels[i] = (uint8_t) level_for(ix->seed, ix->seq + i, m);

@@ -238,9 +238,11 @@ __global__ void __launch_bounds__(CTA_WARPS * 32, 1) scan_cta_kernel(const ScanP
 // expansion), so that the next expansion finds its list and its rows on chip.  Only the source of the bytes changes: the
 // expansion order, the per-row summation order and therefore ids, distances and counters are those of every other kernel.
 struct CtaSmem {
-    int32_t *cbuf, *cslot, *nlist;      // new candidates (ids | positions in the list) | the next expansion's list
-    float *dbuf;
-    volatile int *ctl;                  // 0 cid | 1 nnew | 2 status | 3 next | 5 rows staged | 6 list tag | 8 row tag | 9 parity | 11 next's distance
+    int32_t *cbuf, *cslot, *nlist;      // new candidates (ids | positions in the list), two buffers each | the next expansion's list
+    float *dbuf, *td;                   // distances of the new candidates | RegW::insert_many scratch
+    uint32_t *ti;
+    volatile int *ctl;                  // 0 cid | 1 nnew | 2 status | 3 next | 4 list already filtered | 5 rows staged | 6 list tag | 8 row tag |
+                                        // 9 parity | 11 next's distance | 12 filtered-ahead tag | 13 its nnew | 14 visited count
     uint64_t *mbar;
     char *rows;                         // 32 x row_bytes (row staging enabled) or nullptr
 };
@@ -266,8 +268,9 @@ __device__ __forceinline__ void cta_mbar_wait(uint64_t *bar, uint32_t parity)
 
 template <typename T> __host__ __device__ inline size_t scan_cta_reg_smem(int nvec, size_t row_bytes, bool stage_rows)
 {
-    // query | visited table | cbuf, cslot, nlist, dbuf (32 words each) | control words | mbarrier | staged rows
-    return (((size_t) nvec * Vec<T>::VEC * 4 + (size_t) CTA_SLOTS * 4 + 4 * 128 + 64 + 16 + (stage_rows ? 32 * row_bytes : 0)) + 15) & ~(size_t) 15;
+    // query | visited table | cbuf x2, cslot x2, nlist, dbuf (32 words each) | merge scratch (128 d | 128 id) | control words |
+    // mbarrier | staged rows
+    return (((size_t) nvec * Vec<T>::VEC * 4 + (size_t) CTA_SLOTS * 4 + 6 * 128 + 1024 + 64 + 16 + (stage_rows ? 32 * row_bytes : 0)) + 15) & ~(size_t) 15;
 }
 
 template <typename T, int IP, int NV, int R>
@@ -280,10 +283,13 @@ __device__ __forceinline__ int search_layer_cta_reg(const GraphView &g, RegW<R> 
     const uint32_t row_bytes = (uint32_t) g.row_bytes;
     const unsigned lt_mask = (1u << lane) - 1u;
     volatile int *ctl = S.ctl;
-    if (threadIdx.x == 0) { ctl[6] = -1; ctl[8] = -1; }        // nothing staged yet (read after the first barrier below)
+    if (threadIdx.x == 0) { ctl[6] = -1; ctl[8] = -1; ctl[12] = -1; }      // nothing read ahead yet
+    __syncthreads();
     HB_CTA_PROF_DECL
-    for (;;) {
+    for (int hop = 0;; hop++) {
         HB_CTA_PROF_MARK(4)
+        const int pb = hop & 1;
+        int32_t *cbuf = S.cbuf + 32 * pb, *cslot = S.cslot + 32 * pb;
         if (warp == 0) {
             // nearest unexpanded entry, and the one after it
             int mys = 0x7fffffff, mys2 = 0x7fffffff;
@@ -291,7 +297,7 @@ __device__ __forceinline__ int search_layer_cta_reg(const GraphView &g, RegW<R> 
             for (int r = R - 1; r >= 0; r--)
                 if (!(w.id[r] & EXP_BIT)) { mys2 = mys; mys = lane * R + r; }
             const unsigned b = __ballot_sync(FULL, mys != 0x7fffffff);
-            int cid = -1, nxt = -1;
+            int cid = -1, nxt = -1, pre = 0, nnew = 0, staged = 0;
             float nxd = 0.f;
             if (b) {
                 const int src = __ffs(b) - 1;
@@ -304,44 +310,60 @@ __device__ __forceinline__ int search_layer_cta_reg(const GraphView &g, RegW<R> 
 #pragma unroll
                 for (int r = 0; r < R; r++) if (lane * R + r == idx) w.id[r] |= EXP_BIT;
                 if (lc == 0) ctr.n_hop0++; else ctr.n_hopu++;
+                if (look && ctl[12] == cid) {
+                    // the look-ahead warp already filtered this entry's list through the visited table (it was certain
+                    // to be expanded next): its new candidates wait in this expansion's buffers
+                    pre = 1;
+                    nnew = ctl[13];
+                    vs.added(nnew, false);
+                    ctr.n_dist += nnew;
+                    staged = ctl[8] == cid;
+                }
             }
             HB_CTA_PROF_PRED(cid, nxt)
-            if (lane == 0) { ctl[0] = cid; ctl[3] = nxt; ctl[11] = __float_as_int(nxd); ctl[1] = 0; }
+            if (lane == 0) {
+                ctl[0] = cid; ctl[3] = nxt; ctl[11] = __float_as_int(nxd); ctl[4] = pre;
+                ctl[1] = nnew; ctl[2] = ST_OK; ctl[5] = staged;
+                if (pre) ctl[14] = vs.count;
+            }
         }
         __syncthreads();
         HB_CTA_PROF_MARK(0)
         const int cid = ctl[0];
         if (cid < 0) break;
         const int nxt = ctl[3];
+        const bool pre = ctl[4] != 0;
         const int32_t *list = lc == 0 ? g.nbr0 + (size_t) cid * deg : g.nbru + ((size_t) g.uoff[cid] + (lc - 1)) * g.m;
         int32_t look_nb = -1;              // warp 1: the next expansion's list, in flight until the distances are done
         for (int cb = 0; cb < deg; cb += 32) {
-            if (warp == 0) {
-                int st = ST_OK, nnew = 0, staged = 0;
-                if (cb == 0 && !vs.room(deg)) st = ST_TABLE;
-                if (st == ST_OK) {
-                    const int i = cb + lane;
-                    int32_t nb;
-                    if (look && ctl[6] == cid) nb = S.nlist[lane];           // read ahead by the previous expansion
-                    else nb = i < deg ? list[i] : -1;
-                    bool isnew = false;
-                    if (nb >= 0) isnew = vs.insert((uint32_t) nb, false);
-                    const unsigned nmask = __ballot_sync(FULL, isnew);
-                    if (isnew) {
-                        const int j = __popc(nmask & lt_mask);
-                        S.cbuf[j] = nb;
-                        S.cslot[j] = lane;
-                    }
-                    nnew = __popc(nmask);
-                    vs.added(nnew, false);
-                    ctr.n_dist += nnew;
-                    staged = look && ctl[8] == cid;
-                }
-                if (lane == 0) { ctl[1] = nnew; ctl[2] = st; ctl[5] = staged; }
-            } else if (warp == 1 && look && nxt >= 0) {
+            if (warp == 1 && look && nxt >= 0 && cb == 0)
                 look_nb = lane < deg ? __ldg(g.nbr0 + (size_t) nxt * deg + lane) : -1;
+            if (!pre) {
+                if (warp == 0) {
+                    int st = ST_OK, nnew = 0, staged = 0;
+                    if (cb == 0 && !vs.room(deg)) st = ST_TABLE;
+                    if (st == ST_OK) {
+                        const int i = cb + lane;
+                        int32_t nb;
+                        if (look && ctl[6] == cid) nb = S.nlist[lane];           // read ahead by the previous expansion
+                        else nb = i < deg ? list[i] : -1;
+                        bool isnew = false;
+                        if (nb >= 0) isnew = vs.insert((uint32_t) nb, false);
+                        const unsigned nmask = __ballot_sync(FULL, isnew);
+                        if (isnew) {
+                            const int j = __popc(nmask & lt_mask);
+                            cbuf[j] = nb;
+                            cslot[j] = lane;
+                        }
+                        nnew = __popc(nmask);
+                        vs.added(nnew, false);
+                        ctr.n_dist += nnew;
+                        staged = look && ctl[8] == cid;
+                    }
+                    if (lane == 0) { ctl[1] = nnew; ctl[2] = st; ctl[5] = staged; ctl[14] = vs.count; }
+                }
+                __syncthreads();
             }
-            __syncthreads();
             HB_CTA_PROF_MARK(1)
             if (ctl[2] != ST_OK) return ctl[2];
             const int nnew = ctl[1];
@@ -352,10 +374,10 @@ __device__ __forceinline__ int search_layer_cta_reg(const GraphView &g, RegW<R> 
                 if (j0 + 1 < nnew) {
                     float sd;
                     if (staged) {
-                        const int32_t ids[2] = { S.cslot[j0], S.cslot[j0 + 1] };
+                        const int32_t ids[2] = { cslot[j0], cslot[j0 + 1] };
                         sd = group_distance<T, IP, NV, 2, true>(S.rows, row_bytes, g.nvec, q, ids, lane);
                     } else {
-                        const int32_t ids[2] = { S.cbuf[j0], S.cbuf[j0 + 1] };
+                        const int32_t ids[2] = { cbuf[j0], cbuf[j0 + 1] };
                         sd = group_distance<T, IP, NV, 2>(g.vecs, row_bytes, g.nvec, q, ids, lane);
                     }
                     const float v1 = __shfl_sync(FULL, sd, 16);
@@ -363,27 +385,26 @@ __device__ __forceinline__ int search_layer_cta_reg(const GraphView &g, RegW<R> 
                 } else {
                     float sd;
                     if (staged) {
-                        const int32_t ids[1] = { S.cslot[j0] };
+                        const int32_t ids[1] = { cslot[j0] };
                         sd = group_distance<T, IP, NV, 1, true>(S.rows, row_bytes, g.nvec, q, ids, lane);
                     } else {
-                        const int32_t ids[1] = { S.cbuf[j0] };
+                        const int32_t ids[1] = { cbuf[j0] };
                         sd = group_distance<T, IP, NV, 1>(g.vecs, row_bytes, g.nvec, q, ids, lane);
                     }
                     if (lane == 0) S.dbuf[j0] = sd;
                 }
             }
-            if (warp == 1 && look && cb == 0) {
-                S.nlist[lane] = look_nb;
-                if (lane == 0) ctl[6] = nxt;
-            }
             __syncthreads();
             HB_CTA_PROF_MARK(2)
             if (warp == 0) {
-                // admit and insert in neighbour order, as the sequential loop does
+                // admit and insert in neighbour order, as the sequential loop does (several at once when that is the same)
                 const float myd = lane < nnew ? S.dbuf[lane] : __int_as_float(0x7f800000);
-                const uint32_t cj = lane < nnew ? (uint32_t) S.cbuf[lane] : 0u;
+                const uint32_t cj = lane < nnew ? (uint32_t) cbuf[lane] : 0u;
                 unsigned amask = __ballot_sync(FULL, lane < nnew && (w.L < ef || myd < w.f));
                 int st = ST_OK;
+                if (amask & (amask - 1)) {
+                    if (w.insert_many(myd, cj, amask, ef, lane, S.td, S.ti) == ST_OK) amask = 0;
+                }
                 while (amask && st == ST_OK) {
                     const int sl = __ffs(amask) - 1;
                     amask &= amask - 1;
@@ -393,19 +414,33 @@ __device__ __forceinline__ int search_layer_cta_reg(const GraphView &g, RegW<R> 
                     st = w.insert(ed, eid, ef, lane);
                 }
                 if (lane == 0) ctl[2] = st;
-            } else if (warp == 1 && look && cb == 0 && S.rows != nullptr) {
-                // stage the rows of the expansion that follows -- unless a candidate just evaluated will be expanded first
+            } else if (warp == 1 && look && cb == 0) {
+                // Will the entry read ahead really be expanded next?  Yes unless a candidate just evaluated sorts before it
+                // (W is ordered by (distance, id); entries inserted behind it cannot evict it).  Then its expansion is
+                // certain, and its list can be filtered through the visited table now -- warp 0 only touches registers
+                // in this phase -- and the rows of its new candidates copied into shared memory.
+                // (the list read ahead is first needed here: waiting for it next to warp 0's insertions costs nothing, at the end
+                // of the distance phase it held up all four warps -- profiles/r2_cta_reg_ncu_summary.txt)
+                S.nlist[lane] = look_nb;
+                if (lane == 0) ctl[6] = nxt;
                 bool go = nxt >= 0;
                 if (go) {
                     const float nxd = __int_as_float(ctl[11]);
                     const float myd = lane < nnew ? S.dbuf[lane] : __int_as_float(0x7f800000);
-                    const bool first = lane < nnew && (myd < nxd || (myd == nxd && (uint32_t) S.cbuf[lane] < (uint32_t) nxt));
+                    const bool first = lane < nnew && (myd < nxd || (myd == nxd && (uint32_t) cbuf[lane] < (uint32_t) nxt));
                     go = !__any_sync(FULL, first);
                 }
-                if (go) {
-                    const bool need = look_nb >= 0 && !vs.contains((uint32_t) look_nb);
-                    const int cnt = __popc(__ballot_sync(FULL, need));
-                    if (cnt) {
+                if (go && ctl[14] + deg <= vs.limit) {
+                    const bool need = look_nb >= 0 && vs.insert((uint32_t) look_nb, false);
+                    const unsigned nm = __ballot_sync(FULL, need);
+                    const int cnt = __popc(nm);
+                    if (need) {
+                        const int j = __popc(nm & lt_mask);
+                        S.cbuf[32 * (pb ^ 1) + j] = look_nb;
+                        S.cslot[32 * (pb ^ 1) + j] = lane;
+                    }
+                    bool staged_next = false;
+                    if (S.rows != nullptr && cnt) {
                         if (lk.pending) { cta_mbar_wait(S.mbar, (lk.issued - 1u) & 1u); lk.pending = false; }
                         if (lane == 0) {
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -421,9 +456,10 @@ __device__ __forceinline__ int search_layer_cta_reg(const GraphView &g, RegW<R> 
                         if (lane == 0) ctl[9] = (int) (lk.issued & 1u);
                         lk.issued++;
                         lk.pending = true;
+                        staged_next = true;
                     }
-                    if (lane == 0) ctl[8] = nxt;
-                } else if (lane == 0) ctl[8] = -1;
+                    if (lane == 0) { ctl[12] = nxt; ctl[13] = cnt; ctl[8] = staged_next ? nxt : -1; }
+                } else if (lane == 0) { ctl[12] = -1; ctl[8] = -1; }
             }
             __syncthreads();
             HB_CTA_PROF_MARK(3)
@@ -446,10 +482,12 @@ __global__ void __launch_bounds__(CTA_WARPS * 32, 1) scan_cta_reg_kernel(const S
     vs.set_overflow(nullptr, 0);
     CtaSmem S;
     S.cbuf = reinterpret_cast<int32_t *>(vs.tab + CTA_SLOTS);
-    S.cslot = S.cbuf + 32;
-    S.nlist = S.cslot + 32;
+    S.cslot = S.cbuf + 64;
+    S.nlist = S.cslot + 64;
     S.dbuf = reinterpret_cast<float *>(S.nlist + 32);
-    S.ctl = reinterpret_cast<volatile int *>(S.dbuf + 32);
+    S.td = S.dbuf + 32;
+    S.ti = reinterpret_cast<uint32_t *>(S.td + 128);
+    S.ctl = reinterpret_cast<volatile int *>(S.ti + 128);
     S.mbar = reinterpret_cast<uint64_t *>(const_cast<int *>(S.ctl) + 16);
     S.rows = stage_rows ? reinterpret_cast<char *>(S.mbar + 2) : nullptr;
     if (threadIdx.x == 0) {

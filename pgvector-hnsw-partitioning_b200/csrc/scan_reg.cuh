@@ -104,6 +104,77 @@ template <int R> struct RegW {
         }
         return ST_OK;
     }
+
+    // The candidates flagged in amask (lane j holds candidate j: myd, cj) inserted in ONE step: ranks by ballots, then a
+    // scatter through shared memory (td, ti: CAP entries).  Inserting them one after the other in lane order gives the
+    // same list PROVIDED no candidate's distance equals another key's: then the admission test `ed < f` never meets
+    // equality, whatever was trimmed or skipped on the way lies beyond the final entry ef-1 as well, and the result is
+    // the merge trimmed to ef + ties.  Returns -1 WITHOUT touching the list when that cannot be guaranteed (equal
+    // distances, or the untrimmed merge would not fit): the caller then inserts one at a time.
+    __device__ __forceinline__ int insert_many(float myd, uint32_t cj, unsigned amask, int ef, int lane, float *td, uint32_t *ti)
+    {
+        const int k = __popc(amask);
+        if (L + k > CAP) return -1;
+        int shift[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) shift[r] = 0;
+        const bool mine = (amask >> lane) & 1u;
+        int mypos = 0;
+        bool eq = false;
+        for (unsigned rem = amask; rem; rem &= rem - 1) {
+            const int s = __ffs(rem) - 1;
+            const float ed = __shfl_sync(FULL, myd, s);
+            const uint32_t eid = __shfl_sync(FULL, cj, s);
+            int below = 0;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const bool wlt = d[r] < ed || (d[r] == ed && (id[r] & ID_MASK) < eid);     // this entry stays before the candidate
+                below += __popc(__ballot_sync(FULL, wlt));
+                shift[r] += wlt ? 0 : 1;
+                eq |= d[r] == ed;
+            }
+            if (s == lane) mypos += below;
+            else if (mine) {
+                mypos += (ed < myd || (ed == myd && eid < cj)) ? 1 : 0;
+                eq |= ed == myd;
+            }
+        }
+        if (__any_sync(FULL, eq)) return -1;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int s = lane * R + r;
+            if (s < L) { td[s + shift[r]] = d[r]; ti[s + shift[r]] = id[r]; }
+        }
+        if (mine) { td[mypos] = myd; ti[mypos] = cj; }
+        __syncwarp();
+        L += k;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int s = lane * R + r;
+            const bool in = s < L;
+            d[r] = in ? td[in ? s : 0] : __int_as_float(0x7f800000);
+            id[r] = in ? ti[in ? s : 0] : 0xffffffffu;
+        }
+        __syncwarp();
+        if (L >= ef) {
+            f = get_d(ef - 1);
+            if (L > ef) {
+                int keep = 0;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int s = lane * R + r;
+                    keep += __popc(__ballot_sync(FULL, s >= ef && d[r] == f));
+                }
+                if (ef + keep < L) {
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+                        if (lane * R + r >= ef + keep) { d[r] = __int_as_float(0x7f800000); id[r] = 0xffffffffu; }
+                }
+                L = ef + keep;
+            }
+        }
+        return ST_OK;
+    }
 };
 
 // entry list of the next HnswSearchLayer call = the list's first entry (keep = 1: the scan path)

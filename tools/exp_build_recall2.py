@@ -1,7 +1,7 @@
 """Build-quality A/B against a sequentially built graph prepared off the GPU box: _cache/orc_clu_200000_768.npz (the file
 tests/test_gpu_build.py writes under HB_ORACLE_GRAPH_CACHE=_cache) holds the oracle-built graph of clustered(200000, 768, 256, seed=33); this script regenerates the rows,
 loads that graph into an index, builds GPU graphs under the option sets given, and compares recall@10 over 10 000 queries.
-usage: python tools/exp_build_recall2.py [ef,ef,...] [name:opt=v,opt=v ...]"""
+usage: HB_RECALL_ROWS=200000 python tools/exp_build_recall2.py [ef,ef,...] [name:opt=v,opt=v ...]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -9,7 +9,7 @@ import numpy as np
 import pgvector_hnsw_partitioning_b200 as pkg
 from conftest import clustered
 
-n, dim, nq = 200000, 768, 10000
+n, dim, nq = int(os.environ.get("HB_RECALL_ROWS", "200000")), 768, 10000
 efs = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "40,100").split(",")]
 x = clustered(n, dim, 256, seed=33)
 q = clustered(nq, dim, 256, seed=34)
@@ -19,7 +19,7 @@ def recall_rows(ids, gt):
     return np.array([len(set(ids[i]) & set(gt[i])) / gt.shape[1] for i in range(len(gt))])
 
 
-z = np.load(os.path.join(ROOT, "_cache", "orc_clu_200000_768.npz"))
+z = np.load(os.path.join(ROOT, "_cache", "orc_clu_%d_768.npz" % n))
 
 
 class G:
@@ -29,9 +29,15 @@ class G:
 g = G()
 g.n = n
 g.upper_rows, g.entry, g.entry_level = [int(v) for v in z["meta"]]
-xn = (x.astype(np.float64) / np.sqrt((x.astype(np.float64) ** 2).sum(1, keepdims=True))).astype(np.float32)
+xn = np.empty_like(x)
+for i0 in range(0, n, 65536):
+    c = x[i0:i0 + 65536].astype(np.float64)
+    xn[i0:i0 + 65536] = (c / np.sqrt((c * c).sum(1, keepdims=True))).astype(np.float32)
 g.vecs, g.level, g.nbr0, g.uoff, g.nbru, g.ntids = xn, z["level"], z["nbr0"], z["uoff"], z["nbru"], z["ntids"]
-g.tids = z["tids"]
+if "tids" in z:
+    g.tids = z["tids"]
+else:
+    g.tids = np.zeros((n, 10), np.int64); g.tids[:, 0] = z["tids0"]
 ixo = pkg.HnswIndex(dim, "vector_cosine_ops", 16, 64, capacity=n, seed=1)
 ixo.load_graph(g)
 gt, _ = ixo.bruteforce(q, 10)
