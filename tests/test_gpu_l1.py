@@ -108,3 +108,23 @@ def test_batched_build_recall(oracle, pkg):
     rec = lambda ids: float(np.mean([len(set(ids[i, :10]) & set(gt[i])) / 10 for i in range(nq)]))
     assert rec(ge) >= rec(oe) - 0.005, (rec(ge), rec(oe))
     ix.close()
+
+
+@pytest.mark.parametrize("dim,dtype", [(128, 0), (768, 0), (512, 1)])
+def test_cta_per_query_scan_l1(oracle, pkg, dim, dtype):
+    """the four-warps-per-query kernels (csrc/scan_cta.cuh) under the l1 operator classes: forced for every row length
+    (variant 7), each sub-form, against the oracle and against the warp-per-query kernel."""
+    dt = np.float16 if dtype else np.float32
+    n = 3000
+    x = clustered(n, dim, 24, seed=dim + 3, dtype=dt)
+    q = clustered(80, dim, 24, seed=dim + 4, dtype=dt)
+    orc = oracle.Index(dim, 16, 64, oracle.L1, dtype, oracle.CANON, seed=2)
+    orc.build(x)
+    ix = pkg.HnswIndex(dim, "halfvec_l1_ops" if dtype else "vector_l1_ops", 16, 64, capacity=n, seed=2)
+    ix.load_graph(orc.export())
+    oe, od, oc, _ = orc.search_batch(q, 40, threads=4)
+    for v in (7, 17, 27, 6):
+        ix.set_option("variant", v)
+        e, d, c = ix.search_elements(q, 40)
+        assert (c == oc).all() and (e == oe).all() and (d.view(np.uint32) == od.view(np.uint32)).all(), v
+    ix.close()
