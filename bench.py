@@ -305,7 +305,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "partitioned", "build"])
-    ap.add_argument("--rows", dest="n", type=int, default=1000000)
+    ap.add_argument("--rows", dest="n", type=int, default=0,
+                    help="rows (0 = the configuration's own: 1M for configs[1], --part-rows for --workload partitioned, --build-rows for --workload build)")
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--queries", dest="nq", type=int, default=10000)
     ap.add_argument("--ef", type=int, default=0, help="hnsw.ef_search (0 = smallest of the sweep reaching recall 0.95)")
@@ -343,17 +344,20 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    rows_given = args.n > 0
+    if not rows_given:
+        args.n = 1000000
     n, dim, nq, k = args.n, args.dim, args.nq, 10
     hbm_peak, bf16_peak, peak_kind = peaks()
     ctx = dict(pkg=pkg, torch=torch, dev=dev, rank=rank, local_rank=local_rank, world=world, hbm_peak=hbm_peak, peak_kind=peak_kind)
     base_seed = 20260101 + 1
     if args.workload == "partitioned" and args.impl == "ours":
-        rec = run_partitioned(args, ctx, args.n, args.dim if args.dim != 768 else 128)
+        rec = run_partitioned(args, ctx, args.n if rows_given else args.part_rows, args.dim if args.dim != 768 else 128)
         if rank == 0:
             emit(standalone_line(rec, world, args))
         return finish(torch, world)
     if args.workload == "build" and args.impl == "ours":
-        rec = run_build_partitioned(args, ctx, args.n, args.dim if args.dim != 768 else 1536)
+        rec = run_build_partitioned(args, ctx, args.n if rows_given else args.build_rows, args.dim if args.dim != 768 else 1536)
         if rank == 0:
             emit(standalone_line(rec, world, args))
         return finish(torch, world)
@@ -743,8 +747,9 @@ def run_partitioned(args, ctx, n, dim):
     own = len([p for p in range(P) if p % world == rank])
     return {"metric": "QPS (hash-partitioned, %d partitions, merged top-%d)" % (P, k), "value": round(nq * steps / (ms / 1e3), 1), "unit": "queries/s",
             "steps": steps, "warmup": warmup, "ms_per_step": round(ms / steps, 4), "scaling": "strong", "dtype": "f32",
-            "workload": "configs[2]: %dx%d fp32 L2 in %d hash partitions, m=16, ef_construction=64, ef_search=%d, k=10, %d queries/step, "
-                        "queries on every rank, one ncclAllGather of per-rank top-k + merge" % (n, dim, P, ef, nq),
+            "workload": "%s: %dx%d fp32 L2 in %d hash partitions, m=16, ef_construction=64, ef_search=%d, k=10, %d queries/step, "
+                        "queries on every rank, one ncclAllGather of per-rank top-k + merge"
+                        % ("configs[2]" if (n, dim, P) == (10000000, 128, 8) else "configs[2]-shaped, reduced", n, dim, P, ef, nq),
             "parallelism": "partitions/%d (hb_part_*, %d batches in flight)" % (world, NSLOT), "ef_search": ef, "recall@10": round(rec, 4),
             "roofline": {"bound": "hbm", "achieved": round(gbs_per_gpu, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs_per_gpu / hbm_peak, 4),
                          "traffic": None, "note": "per GPU, algorithmic bytes from the in-kernel counters; every query visits every partition"},
