@@ -59,3 +59,30 @@ def test_ranked_merge_equals_sequential_insertion():
         merged += 1
         assert got == sequential(w, cands, ef), (w, cands, ef)
     assert merged > 10000 and declined > 10000
+
+
+def test_look_ahead_guess_is_certain_when_nothing_sorts_before_it():
+    """csrc/scan_cta.cuh: the look-ahead warp does the NEXT expansion's front half (visited filter, row staging) only
+    when that expansion is certain: the second nearest unexpanded entry of W stays the nearest unexpanded one after
+    this expansion's insertions unless an admitted candidate sorts before it by (distance, id).  Model: W entries are
+    (distance, id, expanded); the pick takes the first unexpanded entry in (distance, id) order."""
+    rng = random.Random(11)
+    sure = 0
+    for _ in range(40000):
+        ef = rng.choice([1, 2, 4, 8, 13])
+        spread = rng.choice([5, 10, 1000])
+        w = trim(sorted((float(rng.randint(0, spread)), i) for i in range(rng.randint(2, ef + 3))), ef)
+        expanded = {e[1] for e in w if rng.random() < 0.5}
+        open_ = [e for e in w if e[1] not in expanded]
+        if len(open_) < 2:
+            continue
+        cur, nxt = open_[0], open_[1]
+        expanded.add(cur[1])
+        cands = [(float(rng.randint(0, spread)) + rng.choice([0, 0.5]), 100 + i) for i in range(rng.randint(0, 7))]
+        if any(c < nxt for c in cands):
+            continue                                            # the kernel does nothing ahead in this case
+        sure += 1
+        after = sequential(w, cands, ef)
+        first_open = next(e for e in after if e[1] not in expanded)
+        assert first_open == nxt, (w, cands, ef, nxt, first_open)
+    assert sure > 5000
